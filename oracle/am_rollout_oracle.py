@@ -1,0 +1,528 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of rl4co's AM rollout hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module, and there only as the *checker*
+(or the timed CPU baseline), never as part of the product path.  The product
+(``rl4co_b200``) must not import anything from ``oracle/``.
+
+What this is: a plain-PyTorch (fp32, CPU or any device) restatement, without
+TensorDict/torchrl/lightning, of the reference functions listed in SURVEY.md
+section 8a.  It uses the *same* library calls the reference uses
+(``F.scaled_dot_product_attention``, ``F.linear``, ``torch.bmm``,
+``F.log_softmax``, ``argmax``) in the *same* order so that on CPU it reproduces
+the reference bit-for-bit on actions/masks and to fp32 round-off on
+rewards/log-probs.
+
+Pinning status: the reference's own tests hold **no** golden values for this
+path (shapes only).  The restatement is therefore pinned
+against outputs of the reference itself: ``tests/golden/make_golden.py`` runs the
+unmodified reference files (via ``oracle/ref_standin.py``) in the build container
+and commits the vectors under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks this module against them everywhere, and
+``tests/test_oracle_vs_reference.py`` re-runs the live reference where
+``/root/reference`` exists.
+
+State is a plain ``dict[str, Tensor]`` with exactly the reference's TensorDict keys,
+dtypes and shapes.  Weights are a ``dict`` keyed like a
+reference ``AttentionModelPolicy.state_dict()``.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------- ops
+# reference: rl4co/utils/ops.py
+
+
+def gather_by_index(src, idx, dim=1, squeeze=True):
+    """rl4co/utils/ops.py:54-66"""
+    expanded_shape = list(src.shape)
+    expanded_shape[dim] = -1
+    idx = idx.view(idx.shape + (1,) * (src.dim() - idx.dim())).expand(expanded_shape)
+    squeeze = idx.size(dim) == 1 and squeeze
+    return src.gather(dim, idx).squeeze(dim) if squeeze else src.gather(dim, idx)
+
+
+def batchify(x, repeats: int):
+    """rl4co/utils/ops.py:10-29 -- start-major repeat: flat index = r * B + b."""
+    if repeats <= 0:
+        return x
+    if isinstance(x, dict):
+        return {k: batchify(v, repeats) for k, v in x.items()}
+    s = x.shape
+    return x.expand(repeats, *s).contiguous().view(s[0] * repeats, *s[1:])
+
+
+def unbatchify(x, repeats: int):
+    """rl4co/utils/ops.py:32-51 -- '(r b) ... -> b r ...'"""
+    if repeats <= 0:
+        return x
+    if isinstance(x, dict):
+        return {k: unbatchify(v, repeats) for k, v in x.items()}
+    s = x.shape
+    return x.view(repeats, s[0] // repeats, *s[1:]).permute(1, 0, *range(2, len(s) + 1))
+
+
+def unbatchify_multi(x, shape):
+    """rl4co/utils/ops.py:45-51 with a tuple shape (e.g. (n_aug, n_start))."""
+    for s in reversed(list(shape)):
+        x = unbatchify(x, s)
+    return x
+
+
+def get_tour_length(ordered_locs):
+    """rl4co/utils/ops.py:77-90 (get_distance + roll + sum)"""
+    nxt = torch.roll(ordered_locs, -1, dims=-2)
+    return (nxt - ordered_locs).norm(p=2, dim=-1).sum(-1)
+
+
+def get_num_starts(num_actions: int, env_name: str) -> int:
+    """rl4co/utils/ops.py:115-125"""
+    return num_actions - 1 if env_name == "cvrp" else num_actions
+
+
+def select_start_nodes(batch: int, num_starts: int, num_loc: int, env_name: str, device=None):
+    """rl4co/utils/ops.py:128-149. ``num_loc`` = generator.num_loc (customers for CVRP)."""
+    sel = torch.arange(num_starts, device=device).repeat_interleave(batch) % num_loc
+    return sel + 1 if env_name == "cvrp" else sel
+
+
+def dihedral_8_augmentation(xy):
+    """rl4co/data/transforms.py:16-38 (aug-major: flat index = a * B + b)."""
+    x, y = xy.split(1, dim=2)
+    zs = [(x, y), (1 - x, y), (x, 1 - y), (1 - x, 1 - y), (y, x), (1 - y, x), (y, 1 - x), (1 - y, 1 - x)]
+    return torch.cat([torch.cat(z, dim=2) for z in zs], dim=0)
+
+
+# --------------------------------------------------------------------------- TSP env
+# reference: rl4co/envs/routing/tsp/env.py
+
+
+def tsp_reset(locs):
+    """tsp/env.py:88-113 (+ torchrl fill of done [B,1], envs/common/base.py:135-143)"""
+    B, N = locs.shape[0], locs.shape[-2]
+    dev = locs.device
+    cur = torch.zeros(B, dtype=torch.int64, device=dev)
+    return {
+        "locs": locs,
+        "first_node": cur,
+        "current_node": cur,
+        "i": torch.zeros(B, 1, dtype=torch.int64, device=dev),
+        "action_mask": torch.ones(B, N, dtype=torch.bool, device=dev),
+        "reward": torch.zeros(B, 1, dtype=torch.float32),
+        "done": torch.zeros(B, 1, dtype=torch.bool, device=dev),
+    }
+
+
+def tsp_step(state, action):
+    """tsp/env.py:60-86"""
+    st = dict(state)
+    current_node = action
+    first_node = current_node if st["i"].all() == 0 else st["first_node"]
+    available = st["action_mask"].scatter(-1, current_node.unsqueeze(-1).expand_as(st["action_mask"]), 0)
+    done = torch.sum(available, dim=-1) == 0
+    st.update(
+        first_node=first_node,
+        current_node=current_node,
+        i=st["i"] + 1,
+        action_mask=available,
+        reward=torch.zeros_like(done),
+        done=done,
+        action=action,
+    )
+    return st
+
+
+def tsp_reward(locs, actions):
+    """tsp/env.py:150-156"""
+    return -get_tour_length(gather_by_index(locs, actions))
+
+
+def tsp_check_solution(actions):
+    """tsp/env.py:158-164"""
+    ok = (torch.arange(actions.size(1)).view(1, -1).expand_as(actions) == actions.sort(1)[0]).all()
+    assert ok, "Invalid tour"
+
+
+# --------------------------------------------------------------------------- CVRP env
+# reference: rl4co/envs/routing/cvrp/env.py
+
+
+def cvrp_action_mask(st):
+    """cvrp/env.py:126-136"""
+    exceeds_cap = st["demand"] + st["used_capacity"] > st["vehicle_capacity"] + 1e-5
+    mask_loc = st["visited"][..., 1:].to(exceeds_cap.dtype) | exceeds_cap
+    mask_depot = (st["current_node"] == 0) & ((mask_loc == 0).int().sum(-1) > 0)[:, None]
+    return ~torch.cat((mask_depot, mask_loc), -1)
+
+
+def cvrp_reset(depot, locs, demand, vehicle_capacity: float = 1.0):
+    """cvrp/env.py:98-124 (demand already divided by capacity, generator.py:136)"""
+    B = locs.shape[0]
+    dev = locs.device
+    st = {
+        "locs": torch.cat((depot[:, None, :], locs), -2),
+        "demand": demand,
+        "current_node": torch.zeros(B, 1, dtype=torch.long, device=dev),
+        "used_capacity": torch.zeros(B, 1, device=dev),
+        "vehicle_capacity": torch.full((B, 1), vehicle_capacity, device=dev),
+        "visited": torch.zeros(B, locs.shape[-2] + 1, dtype=torch.uint8, device=dev),
+    }
+    st["action_mask"] = cvrp_action_mask(st)
+    st["done"] = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+    return st
+
+
+def cvrp_step(state, action):
+    """cvrp/env.py:66-96"""
+    st = dict(state)
+    current_node = action[:, None]
+    n_loc = st["demand"].size(-1)
+    selected_demand = gather_by_index(st["demand"], torch.clamp(current_node - 1, 0, n_loc - 1), squeeze=False)
+    used_capacity = (st["used_capacity"] + selected_demand) * (current_node != 0).float()
+    visited = st["visited"].scatter(-1, current_node, 1)
+    done = visited.sum(-1) == visited.size(-1)
+    st.update(
+        current_node=current_node,
+        used_capacity=used_capacity,
+        visited=visited,
+        reward=torch.zeros_like(done),
+        done=done,
+        action=action,
+    )
+    st["action_mask"] = cvrp_action_mask(st)
+    return st
+
+
+def cvrp_reward(locs_with_depot, actions):
+    """cvrp/env.py:138-147"""
+    ordered = torch.cat([locs_with_depot[..., 0:1, :], gather_by_index(locs_with_depot, actions)], dim=1)
+    return -get_tour_length(ordered)
+
+
+def cvrp_check_solution(st, actions):
+    """cvrp/env.py:149-177"""
+    batch_size, graph_size = st["demand"].size()
+    sorted_pi = actions.sort(1)[0]
+    ok = (
+        torch.arange(1, graph_size + 1).view(1, -1).expand(batch_size, graph_size) == sorted_pi[:, -graph_size:]
+    ).all() and (sorted_pi[:, :-graph_size] == 0).all()
+    assert ok, "Invalid tour"
+    demand_with_depot = torch.cat((-st["vehicle_capacity"], st["demand"]), 1)
+    d = demand_with_depot.gather(1, actions)
+    used = torch.zeros_like(st["demand"][:, 0])
+    for i in range(actions.size(1)):
+        used = used + d[:, i]
+        used[used < 0] = 0
+        assert (used <= st["vehicle_capacity"][:, 0] + 1e-5).all(), "Used more than capacity"
+
+
+ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset}
+ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step}
+
+
+def env_reset(env_name, inst):
+    """inst: dict with 'locs' (tsp) or 'depot','locs','demand' (cvrp; generator output keys)."""
+    if env_name == "tsp":
+        return tsp_reset(inst["locs"])
+    return cvrp_reset(inst["depot"], inst["locs"], inst["demand"])
+
+
+def env_reward(env_name, st, actions):
+    return tsp_reward(st["locs"], actions) if env_name == "tsp" else cvrp_reward(st["locs"], actions)
+
+
+# --------------------------------------------------------------------------- generators
+# reference: rl4co/envs/routing/tsp/generator.py:49-58, cvrp/generator.py:15-30,114-140
+
+CAPACITIES = {10: 20.0, 15: 25.0, 20: 30.0, 30: 33.0, 40: 37.0, 50: 40.0, 60: 43.0, 75: 45.0,
+              100: 50.0, 125: 55.0, 150: 60.0, 200: 70.0, 500: 100.0, 1000: 150.0}
+
+
+def generate_instances(env_name, batch, num_loc, generator=None):
+    """Uniform(0,1) sampling exactly as torch.distributions.Uniform(...).sample does
+    (rand * (high-low) + low), in the generator's call order."""
+    def uni(shape, low, high):
+        return torch.rand(shape, generator=generator) * (high - low) + low
+
+    if env_name == "tsp":
+        return {"locs": uni((batch, num_loc, 2), 0.0, 1.0)}
+    locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
+    demand = uni((batch, num_loc), 0.0, 9.0)
+    demand = (demand.int() + 1).float()
+    cap = CAPACITIES.get(num_loc) or CAPACITIES[min(CAPACITIES, key=lambda x: abs(x - num_loc))]
+    return {"locs": locs[:, 1:, :], "depot": locs[:, 0, :], "demand": demand / cap,
+            "capacity": torch.full((batch, 1), cap)}
+
+
+# --------------------------------------------------------------------------- decoder
+# reference: rl4co/models/zoo/am/decoder.py, nn/env_embeddings/context.py, nn/attention.py
+
+def _w(weights, key):
+    return weights["decoder." + key] if ("decoder." + key) in weights else weights[key]
+
+
+def precompute_cache(weights, h, use_graph_context=True):
+    """am/decoder.py:201-228"""
+    k, v, l = F.linear(h, _w(weights, "project_node_embeddings.weight")).chunk(3, dim=-1)
+    g = F.linear(h.mean(1), _w(weights, "project_fixed_context.weight")) if use_graph_context else 0
+    return {"node_embeddings": h, "graph_context": g, "glimpse_key": k, "glimpse_val": v, "logit_key": l}
+
+
+def tsp_context(weights, emb, st):
+    """nn/env_embeddings/context.py:116-134 (TSPContext.forward)"""
+    B = emb.size(0)
+    wp = _w(weights, "context_embedding.W_placeholder")
+    first = st["first_node"]
+    node_dim = (-1,) if first.dim() == 1 else (first.size(-1), -1)
+    if st["i"][(0,) * st["i"].dim()].item() < 1:
+        if first.dim() == 1:
+            ctx = wp[None, :].expand(B, wp.size(-1))
+        else:
+            ctx = wp[None, None, :].expand(B, first.size(1), wp.size(-1))
+    else:
+        ctx = gather_by_index(emb, torch.stack([first, st["current_node"]], -1).view(B, -1)).view(B, *node_dim)
+    return F.linear(ctx, _w(weights, "context_embedding.project_context.weight"))
+
+
+def vrp_context(weights, emb, st):
+    """nn/env_embeddings/context.py:61-74,137-149 (EnvContext.forward + VRPContext)"""
+    cur = gather_by_index(emb, st["current_node"])
+    state_emb = st["vehicle_capacity"] - st["used_capacity"]
+    return F.linear(torch.cat([cur, state_emb], -1), _w(weights, "context_embedding.project_context.weight"))
+
+
+def pointer_logits(weights, q, K, V, L, mask, num_heads=8):
+    """nn/attention.py:274-320 (PointerAttention.forward, mask_inner=True, no out bias)"""
+    def heads(x):  # "... g (h s) -> ... h g s"
+        return x.view(*x.shape[:-1], num_heads, -1).transpose(-2, -3)
+
+    attn_mask = mask.unsqueeze(1) if mask.ndim == 3 else mask.unsqueeze(1).unsqueeze(2)
+    o = F.scaled_dot_product_attention(heads(q), heads(K), heads(V), attn_mask=attn_mask)
+    o = o.transpose(-2, -3)
+    o = o.reshape(*o.shape[:-2], -1)  # "... h n g -> ... n (h g)"
+    glimpse = F.linear(o, _w(weights, "pointer.project_out.weight"))
+    logits = torch.bmm(glimpse, L.squeeze(-2).transpose(-2, -1)).squeeze(-2) / math.sqrt(glimpse.size(-1))
+    assert not torch.isnan(logits).any(), "Logits contain NaNs"
+    return logits
+
+
+def decoder_forward(weights, env_name, st, cache, num_starts=0, faithful_copies=True):
+    """am/decoder.py:128-193 (AttentionModelDecoder.forward; static dynamic-embedding)"""
+    if num_starts > 1:
+        st = {k: unbatchify(v, num_starts) for k, v in st.items() if k != "reward"}
+    emb, g = cache["node_embeddings"], cache["graph_context"]
+    two_batch_dims = st["action_mask"].dim() == 3
+    if two_batch_dims and isinstance(g, torch.Tensor):
+        g = g.unsqueeze(1)
+    ctx = tsp_context(weights, emb, st) if env_name == "tsp" else vrp_context(weights, emb, st)
+    q = ctx + g
+    q = q.unsqueeze(1) if q.ndim == 2 else q
+    K, V, L = cache["glimpse_key"], cache["glimpse_val"], cache["logit_key"]
+    if faithful_copies:  # `stat + 0` materialises 3 copies per step, am/decoder.py:149-152
+        K, V, L = K + 0, V + 0, L + 0
+    mask = st["action_mask"]
+    logits = pointer_logits(weights, q, K, V, L, mask)
+    if num_starts > 1:  # "b s l -> (s b) l", am/decoder.py:190-192
+        logits = logits.transpose(0, 1).reshape(-1, logits.size(-1))
+        mask = mask.transpose(0, 1).reshape(-1, mask.size(-1))
+    return logits, mask
+
+
+# --------------------------------------------------------------------------- decoding strategy
+# reference: rl4co/utils/decoding.py
+
+
+def process_logits(logits, mask, temperature=1.0, tanh_clipping=10.0, mask_logits=True):
+    """utils/decoding.py:138-188 (top-k / top-p off)"""
+    if tanh_clipping > 0:
+        logits = torch.tanh(logits) * tanh_clipping
+    if mask_logits:
+        logits[~mask] = float("-inf")
+    logits = logits / temperature
+    return F.log_softmax(logits, dim=-1)
+
+
+def select_greedy(logprobs, mask):
+    """utils/decoding.py:387-397"""
+    sel = logprobs.argmax(dim=-1)
+    assert not (~mask).gather(1, sel.unsqueeze(-1)).any(), "infeasible action selected"
+    return sel
+
+
+def select_sampling(logprobs, mask, noise=None, generator=None):
+    """utils/decoding.py:399-413.  ``torch.multinomial(p, 1)`` is, in ATen,
+    ``argmax(p / q)`` with ``q = empty_like(p).exponential_(1)`` (the n_sample==1 path of
+    aten/src/ATen/native/Distributions.cpp multinomial); passing ``noise=q`` makes the draw
+    reproducible across devices."""
+    probs = logprobs.exp()
+    if noise is None:
+        sel = torch.multinomial(probs, 1, generator=generator).squeeze(1)
+    else:
+        sel = (probs / noise).argmax(dim=-1)
+    assert not (~mask).gather(1, sel.unsqueeze(-1)).any(), "infeasible action selected"
+    return sel
+
+
+def get_log_likelihood(logprobs):
+    """utils/decoding.py:38-62 (per-step logprobs already gathered)"""
+    assert (logprobs > -1000).all(), "Logprobs should not be -inf, check sampling procedure!"
+    return logprobs.sum(1)
+
+
+# --------------------------------------------------------------------------- rollout loop
+# reference: rl4co/models/common/constructive/base.py:192-251
+
+
+def rollout(weights, env_name, inst, h, decode_type="greedy", num_starts=None, actions=None,
+            noise=None, use_graph_context=True, temperature=1.0, tanh_clipping=10.0,
+            return_trace=False, faithful_copies=True, num_loc=None, generator=None):
+    """Decode loop of ConstructivePolicy.forward from encoder output ``h`` on.
+
+    decode_type: greedy | sampling | multistart_greedy | multistart_sampling | evaluate
+    actions    : [B,T] teacher-forced actions (forces decode_type="evaluate")
+    noise      : callable(step, shape) -> Exp(1) tensor, or None to use torch.multinomial
+    returns dict(reward[B'], log_likelihood[B'], actions[B',T], logprobs[B',T], state, trace?)
+    """
+    if actions is not None:
+        decode_type = "evaluate"
+    multistart = "multistart" in decode_type
+    st = env_reset(env_name, inst)
+    B = st["locs"].shape[0]
+    step_fn = ENV_STEP[env_name]
+    acts, lps = [], []
+    trace = {"mask": [], "logits": [], "logprobs": []} if return_trace else None
+
+    # pre_decoder_hook, utils/decoding.py:282-330
+    S = 0
+    if multistart:
+        S = num_starts if num_starts is not None else get_num_starts(st["action_mask"].shape[-1], env_name)
+        if S > 1 or num_starts is None:
+            nl = num_loc if num_loc is not None else (st["locs"].shape[1] - (1 if env_name == "cvrp" else 0))
+            a0 = select_start_nodes(B, S, nl, env_name, device=st["locs"].device)
+            st = {k: batchify(v, S) for k, v in st.items()}
+            st = step_fn(st, a0)
+            lps.append(torch.zeros_like(a0, dtype=torch.float32))
+            acts.append(a0)
+        else:
+            S = 0
+    cache = precompute_cache(weights, h, use_graph_context)
+
+    step = 0
+    while not st["done"].all():
+        logits, mask = decoder_forward(weights, env_name, st, cache, S, faithful_copies)
+        if return_trace:
+            trace["mask"].append(mask.clone())
+            trace["logits"].append(logits.clone())
+        logprobs = process_logits(logits, mask, temperature, tanh_clipping)
+        if decode_type == "evaluate":
+            a = actions[..., step]
+        elif "greedy" in decode_type:
+            a = select_greedy(logprobs, mask)
+        else:
+            q = noise(step, logprobs.shape) if noise is not None else None
+            a = select_sampling(logprobs, mask, q, generator)
+        if return_trace:
+            trace["logprobs"].append(logprobs.clone())
+        lps.append(gather_by_index(logprobs, a, dim=1))
+        acts.append(a)
+        st = step_fn(st, a)
+        step += 1
+
+    logprobs = torch.stack(lps, 1)
+    out_actions = torch.stack(acts, 1)
+    out = {
+        "reward": env_reward(env_name, st, out_actions),
+        "log_likelihood": get_log_likelihood(logprobs),
+        "actions": out_actions,
+        "logprobs": logprobs,
+        "state": st,
+    }
+    if return_trace:
+        out["trace"] = trace
+    return out
+
+
+# --------------------------------------------------------------------------- encoder
+# reference: rl4co/models/zoo/am/encoder.py:68-87, nn/env_embeddings/init.py:55-68,115-136,
+#            nn/graph/attnnet.py:16-106, nn/attention.py:64-134, nn/ops.py:30-54
+
+
+def init_embedding(weights, env_name, st):
+    p = "encoder.init_embedding."
+    if env_name == "tsp":
+        return F.linear(st["locs"], weights[p + "init_embed.weight"], weights[p + "init_embed.bias"])
+    depot, cities = st["locs"][:, :1, :], st["locs"][:, 1:, :]
+    de = F.linear(depot, weights[p + "init_embed_depot.weight"], weights[p + "init_embed_depot.bias"])
+    ne = F.linear(torch.cat((cities, st["demand"][..., None]), -1), weights[p + "init_embed.weight"],
+                  weights[p + "init_embed.bias"])
+    return torch.cat((de, ne), -2)
+
+
+def _normalization(weights, prefix, x, kind):
+    w, b = weights[prefix + "normalizer.weight"], weights[prefix + "normalizer.bias"]
+    if kind == "batch":  # eval mode: running stats
+        y = F.batch_norm(x.reshape(-1, x.size(-1)), weights[prefix + "normalizer.running_mean"],
+                         weights[prefix + "normalizer.running_var"], w, b, training=False, eps=1e-5)
+        return y.view(*x.size())
+    if kind == "instance":
+        return F.instance_norm(x.permute(0, 2, 1), weight=w, bias=b, eps=1e-5).permute(0, 2, 1)
+    raise ValueError(kind)
+
+
+def encoder_forward(weights, env_name, st, num_layers=3, num_heads=8, normalization="batch"):
+    h = init_embedding(weights, env_name, st)
+    init_h = h
+    for i in range(num_layers):
+        p = f"encoder.net.layers.{i}."
+        qkv = F.linear(h, weights[p + "0.module.Wqkv.weight"], weights[p + "0.module.Wqkv.bias"])
+        B, N, _ = qkv.shape
+        q, k, v = qkv.view(B, N, 3, num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+        o = F.scaled_dot_product_attention(q, k, v)
+        o = o.transpose(1, 2).reshape(B, N, -1)
+        h = h + F.linear(o, weights[p + "0.module.out_proj.weight"], weights[p + "0.module.out_proj.bias"])
+        h = _normalization(weights, p + "1.", h, normalization)
+        f = F.relu(F.linear(h, weights[p + "2.module.lins.0.weight"], weights[p + "2.module.lins.0.bias"]))
+        h = h + F.linear(f, weights[p + "2.module.lins.1.weight"], weights[p + "2.module.lins.1.bias"])
+        h = _normalization(weights, p + "3.", h, normalization)
+    return h, init_h
+
+
+def policy_forward(weights, env_name, inst, decode_type="greedy", num_layers=3, normalization="batch", **kw):
+    """ConstructivePolicy.forward, constructive/base.py:154-263 (encoder + rollout)."""
+    st0 = env_reset(env_name, inst)
+    h, _ = encoder_forward(weights, env_name, st0, num_layers=num_layers, normalization=normalization)
+    return rollout(weights, env_name, inst, h, decode_type=decode_type, **kw)
+
+
+# --------------------------------------------------------------------------- REINFORCE / POMO glue
+# reference: rl4co/models/rl/reinforce/reinforce.py:71-111, baselines.py:55-81, zoo/pomo/model.py:88-143
+
+
+def reinforce_loss(reward, log_likelihood, baseline_value):
+    """reinforce.py:96-104: advantage = reward - bl ; loss = -(adv * ll).mean()"""
+    advantage = reward - baseline_value
+    return -(advantage * log_likelihood).mean()
+
+
+def shared_baseline(reward, num_starts):
+    """baselines.py:55-61 SharedBaseline.eval: mean over the starts of each instance."""
+    r = unbatchify(reward, num_starts)
+    return r.mean(dim=1, keepdim=True)
+
+
+def mean_baseline(reward):
+    """baselines.py:75-81 (ExponentialBaseline first call / MeanBaseline): reward.mean()"""
+    return reward.mean()
+
+
+def pomo_reduce(reward, n_aug, n_start):
+    """zoo/pomo/model.py:103-136: [aug*start*B] -> max over starts, then max over augs."""
+    r = unbatchify_multi(reward, (n_aug, n_start)) if n_aug > 1 else unbatchify(reward, n_start).unsqueeze(1)
+    max_reward, _ = r.max(dim=-1)
+    max_aug_reward, _ = max_reward.max(dim=1)
+    return max_reward, max_aug_reward

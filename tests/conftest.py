@@ -1,0 +1,61 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """npz fixture produced by tests/golden/make_golden.py from the live reference."""
+
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+    def __getitem__(self, k):
+        return torch.from_numpy(self.z[k])
+
+    def __contains__(self, k):
+        return k in self.z.files
+
+    def weights(self, device="cpu"):
+        return {k[3:]: torch.from_numpy(self.z[k]).to(device) for k in self.z.files if k.startswith("w::")}
+
+    def inst(self, device="cpu"):
+        return {k[6:]: torch.from_numpy(self.z[k]).to(device) for k in self.z.files if k.startswith("inst::")}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def _get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+
+    return _get
+
+
+def env_of(name):
+    return "tsp" if "tsp" in name else "cvrp"

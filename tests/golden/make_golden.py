@@ -1,0 +1,211 @@
+"""Generate the golden vectors under tests/golden/ by executing rl4co's OWN, unmodified
+hot-path files from /root/reference (through oracle/ref_standin.py -- container stubs for
+tensordict/torchrl/lightning only, no arithmetic).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every array written here is produced by reference code + PyTorch CPU fp32.  The fixtures
+pin (a) the env MDP (masks / visited / capacity / done / reward) under the reference's
+``random_policy`` rollout, (b) the AM decoder path (raw logits per step, log-probs,
+actions, reward, log-likelihood) for greedy, sampling-with-recorded-Exp(1)-noise,
+multistart-greedy and teacher-forced evaluation, (c) the AM encoder, and (d) the
+batchify / dihedral-8 layout conventions.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_standin  # noqa: E402
+
+ref = ref_standin.load()
+TensorDict = ref.TensorDict
+
+
+def npy(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def make_env(name, n, check=True):
+    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    return Env(generator_params=dict(num_loc=n), check_solution=check)
+
+
+def env_fixture(name, n, batch, seed):
+    """Reference env driven by the reference's random_policy (utils/decoding.py:78-106)."""
+    torch.manual_seed(seed)
+    env = make_env(name, n)
+    td0 = env.generator(batch_size=[batch])
+    out = {f"inst::{k}": npy(td0[k]) for k in td0.keys()}
+    td = env.reset(td0.clone())
+    masks, dones, visited, used, cur = [npy(td["action_mask"])], [], [], [], []
+    actions = []
+    while not td["done"].all():
+        td = ref.decoding.random_policy(td)
+        actions.append(td["action"].clone())
+        td = env.step(td)["next"]
+        masks.append(npy(td["action_mask"]))
+        dones.append(npy(td["done"]))
+        cur.append(npy(td["current_node"]).reshape(batch))
+        if name == "cvrp":
+            visited.append(npy(td["visited"]))
+            used.append(npy(td["used_capacity"]))
+    actions = torch.stack(actions, 1)
+    reward = env.get_reward(td, actions)  # runs check_solution_validity too
+    out.update(actions=npy(actions), action_mask=np.stack(masks), done=np.stack(dones),
+               current_node=np.stack(cur), reward=npy(reward))
+    if name == "cvrp":
+        out.update(visited=np.stack(visited), used_capacity=np.stack(used))
+    else:
+        out.update(first_node=npy(td["first_node"]), i=npy(td["i"]))
+    return out
+
+
+class Recorder:
+    """Forward hook on the reference decoder recording raw (logits, mask) per step."""
+
+    def __init__(self, decoder):
+        self.logits, self.masks = [], []
+        self.h = decoder.register_forward_hook(self._hook)
+
+    def _hook(self, mod, args, output):
+        self.logits.append(output[0].detach().clone())
+        self.masks.append(output[1].detach().clone())
+
+    def pop(self):
+        lg, mk = torch.stack(self.logits), torch.stack(self.masks)
+        self.logits, self.masks = [], []
+        return npy(lg), npy(mk)
+
+
+def am_fixture(name, n, batch, seed, ms_batch=3):
+    torch.manual_seed(seed)
+    env = make_env(name, n)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    # make the decoder more "opinionated" than default init so that argmax margins are healthy
+    out = {}
+    for k, v in pol.state_dict().items():
+        if k.startswith("decoder."):
+            out["w::" + k] = npy(v)
+    td0 = env.generator(batch_size=[batch])
+    for k in td0.keys():
+        out[f"inst::{k}"] = npy(td0[k])
+    rec = Recorder(pol.decoder)
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        h, _ = pol.encoder(td)
+        out["h"] = npy(h)
+        # -- greedy
+        o = pol(td.clone(), env, phase="test", decode_type="greedy", return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        out.update(greedy_actions=npy(o["actions"]), greedy_logprobs=npy(o["log_likelihood"]),
+                   greedy_reward=npy(o["reward"]), greedy_logits=lg, greedy_masks=mk)
+        # -- sampling; the Exp(1) draws consumed by torch.multinomial are regenerated
+        torch.manual_seed(seed + 1)
+        o = pol(td.clone(), env, phase="train", decode_type="sampling", return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        T = o["actions"].shape[1]
+        torch.manual_seed(seed + 1)
+        q = torch.stack([torch.empty(batch, lg.shape[-1]).exponential_(1) for _ in range(T)])
+        out.update(sampling_actions=npy(o["actions"]), sampling_logprobs=npy(o["log_likelihood"]),
+                   sampling_reward=npy(o["reward"]), sampling_noise=npy(q), sampling_logits=lg)
+        # -- teacher-forced evaluation of an independent (random-policy) action sequence
+        torch.manual_seed(seed + 2)
+        tdr = env.reset(td0.clone())
+        acts = []
+        while not tdr["done"].all():
+            tdr = ref.decoding.random_policy(tdr)
+            acts.append(tdr["action"].clone())
+            tdr = env.step(tdr)["next"]
+        acts = torch.stack(acts, 1)
+        o = pol(td.clone(), env, phase="train", actions=acts, return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        out.update(eval_actions=npy(acts), eval_logprobs=npy(o["log_likelihood"]), eval_reward=npy(o["reward"]),
+                   eval_logits=lg)
+        # -- multistart greedy on the first ms_batch instances (start-major layout)
+        tdm = env.reset(td0[:ms_batch].clone())
+        o = pol(tdm.clone(), env, phase="test", decode_type="multistart_greedy", return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        out.update(ms_actions=npy(o["actions"]), ms_logprobs=npy(o["log_likelihood"]), ms_reward=npy(o["reward"]),
+                   ms_logits=lg, ms_batch=np.int64(ms_batch))
+        # -- POMO-style: no graph context (pomo/model.py:59-63)
+        polp = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1, use_graph_context=False).eval()
+        polp.load_state_dict(pol.state_dict())
+        o = polp(tdm.clone(), env, phase="test", decode_type="multistart_greedy", return_sum_log_likelihood=False)
+        out.update(pomo_actions=npy(o["actions"]), pomo_logprobs=npy(o["log_likelihood"]), pomo_reward=npy(o["reward"]))
+    return out
+
+
+def encoder_fixture(name, n, batch, seed, normalization):
+    torch.manual_seed(seed)
+    env = make_env(name, n)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1, normalization=normalization).eval()
+    if normalization == "batch":  # non-trivial running stats
+        for m in pol.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+    out = {"w::" + k: npy(v) for k, v in pol.state_dict().items()
+           if k.startswith("encoder.") and "num_batches" not in k}
+    td0 = env.generator(batch_size=[batch])
+    for k in td0.keys():
+        out[f"inst::{k}"] = npy(td0[k])
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        h, init_h = pol.encoder(td)
+    out.update(h=npy(h), init_h=npy(init_h))
+    return out
+
+
+def layout_fixture():
+    torch.manual_seed(11)
+    x = torch.rand(3, 5, 2)
+    aug = ref.transforms.dihedral_8_augmentation(x)
+    td = TensorDict({"locs": x.clone()}, batch_size=[3])
+    sa = ref.transforms.StateAugmentation(num_augment=8, augment_fn="dihedral8")(td)
+    b = ref.ops.batchify(x, 4)
+    r = torch.arange(3 * 8 * 4, dtype=torch.float32)
+    ub = ref.ops.unbatchify(r, (8, 4))
+    env = make_env("tsp", 5)
+    envc = make_env("cvrp", 5)
+    tdx = env.reset(batch_size=[3])
+    tdc = envc.reset(batch_size=[3])
+    return dict(x=npy(x), dihedral8=npy(aug), state_aug=npy(sa["locs"]), batchify4=npy(b),
+                unbatchify_8_4=npy(ub), tsp_starts=npy(env.select_start_nodes(tdx, 5)),
+                cvrp_starts=npy(envc.select_start_nodes(tdc, 5)),
+                tsp_num_starts=np.int64(env.get_num_starts(tdx)), cvrp_num_starts=np.int64(envc.get_num_starts(tdc)))
+
+
+def main():
+    jobs = {
+        "env_tsp20": lambda: env_fixture("tsp", 20, 16, 100),
+        "env_tsp50": lambda: env_fixture("tsp", 50, 8, 101),
+        "env_cvrp20": lambda: env_fixture("cvrp", 20, 16, 102),
+        "env_cvrp50": lambda: env_fixture("cvrp", 50, 8, 103),
+        "am_tsp20": lambda: am_fixture("tsp", 20, 8, 200),
+        "am_cvrp20": lambda: am_fixture("cvrp", 20, 8, 201),
+        "am_tsp50": lambda: am_fixture("tsp", 50, 4, 202, ms_batch=2),
+        "am_cvrp50": lambda: am_fixture("cvrp", 50, 4, 203, ms_batch=2),
+        "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
+        "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
+        "layout": layout_fixture,
+    }
+    for name, fn in jobs.items():
+        data = fn()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: {len(data)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

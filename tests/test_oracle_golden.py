@@ -1,0 +1,117 @@
+"""CPU: pin oracle/am_rollout_oracle.py against the golden vectors recorded from the
+unmodified reference (tests/golden/make_golden.py)."""
+
+import pytest
+import torch
+
+from oracle import am_rollout_oracle as O
+from conftest import env_of
+
+ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50"]
+AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50"]
+
+
+@pytest.mark.parametrize("name", ENV_FIX)
+def test_env_mdp_bit_exact(golden, name):
+    g = golden(name)
+    env = env_of(name)
+    st = O.env_reset(env, g.inst())
+    actions = g["actions"]
+    assert torch.equal(st["action_mask"], g["action_mask"][0])
+    for t in range(actions.shape[1]):
+        st = O.ENV_STEP[env](st, actions[:, t])
+        assert torch.equal(st["action_mask"], g["action_mask"][t + 1]), f"mask step {t}"
+        assert torch.equal(st["done"], g["done"][t]), f"done step {t}"
+        assert torch.equal(st["current_node"].reshape(-1), g["current_node"][t])
+        if env == "cvrp":
+            assert torch.equal(st["visited"], g["visited"][t])
+            assert torch.equal(st["used_capacity"], g["used_capacity"][t])
+    if env == "tsp":
+        assert torch.equal(st["first_node"], g["first_node"])
+        assert torch.equal(st["i"], g["i"])
+        O.tsp_check_solution(actions)
+    else:
+        O.cvrp_check_solution(st, actions)
+    r = O.env_reward(env, st, actions)
+    assert torch.equal(r, g["reward"])
+
+
+@pytest.mark.parametrize("name", AM_FIX)
+def test_am_greedy(golden, name):
+    g = golden(name)
+    out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], "greedy", return_trace=True)
+    assert torch.equal(out["actions"], g["greedy_actions"])
+    torch.testing.assert_close(torch.stack(out["trace"]["logits"]), g["greedy_logits"], rtol=1e-6, atol=1e-6)
+    assert torch.equal(torch.stack(out["trace"]["mask"]), g["greedy_masks"])
+    torch.testing.assert_close(out["logprobs"], g["greedy_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], g["greedy_reward"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", AM_FIX)
+def test_am_sampling_with_recorded_noise(golden, name):
+    g = golden(name)
+    q = g["sampling_noise"]
+    out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], "sampling", noise=lambda t, shape: q[t])
+    assert torch.equal(out["actions"], g["sampling_actions"])
+    torch.testing.assert_close(out["logprobs"], g["sampling_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], g["sampling_reward"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", AM_FIX)
+def test_am_teacher_forced(golden, name):
+    g = golden(name)
+    out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], actions=g["eval_actions"], return_trace=True)
+    torch.testing.assert_close(torch.stack(out["trace"]["logits"]), g["eval_logits"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out["logprobs"], g["eval_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], g["eval_reward"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", AM_FIX)
+def test_am_multistart_and_pomo(golden, name):
+    g = golden(name)
+    mb = int(g["ms_batch"])
+    inst = {k: v[:mb] for k, v in g.inst().items()}
+    out = O.rollout(g.weights(), env_of(name), inst, g["h"][:mb], "multistart_greedy")
+    assert torch.equal(out["actions"], g["ms_actions"])
+    torch.testing.assert_close(out["logprobs"], g["ms_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], g["ms_reward"], rtol=1e-6, atol=0)
+    out = O.rollout(g.weights(), env_of(name), inst, g["h"][:mb], "multistart_greedy", use_graph_context=False)
+    assert torch.equal(out["actions"], g["pomo_actions"])
+    torch.testing.assert_close(out["logprobs"], g["pomo_logprobs"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,norm", [("enc_tsp20_batch", "batch"), ("enc_cvrp20_instance", "instance")])
+def test_encoder(golden, name, norm):
+    g = golden(name)
+    env = env_of(name)
+    st = O.env_reset(env, g.inst())
+    h, init_h = O.encoder_forward(g.weights(), env, st, num_layers=1, normalization=norm)
+    torch.testing.assert_close(init_h, g["init_h"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(h, g["h"], rtol=1e-5, atol=1e-5)
+
+
+def test_layout_conventions(golden):
+    g = golden("layout")
+    x = g["x"]
+    assert torch.equal(O.dihedral_8_augmentation(x), g["dihedral8"])
+    assert torch.equal(O.dihedral_8_augmentation(O.batchify(x, 8)[: x.shape[0]]), g["state_aug"])
+    assert torch.equal(O.batchify(x, 4), g["batchify4"])
+    r = torch.arange(3 * 8 * 4, dtype=torch.float32)
+    assert torch.equal(O.unbatchify_multi(r, (8, 4)), g["unbatchify_8_4"])
+    assert torch.equal(O.select_start_nodes(3, 5, 5, "tsp"), g["tsp_starts"])
+    assert torch.equal(O.select_start_nodes(3, 5, 5, "cvrp"), g["cvrp_starts"])
+    assert O.get_num_starts(5, "tsp") == int(g["tsp_num_starts"])
+    assert O.get_num_starts(6, "cvrp") == int(g["cvrp_num_starts"])
+
+
+def test_pomo_reduce_and_loss():
+    torch.manual_seed(0)
+    B, A, S = 3, 8, 5
+    r = torch.randn(A * S * B)
+    mr, mar = O.pomo_reduce(r, A, S)
+    rr = r.view(S, A, B).permute(2, 1, 0)  # flat index = s*(A*B) + a*B + b
+    assert torch.equal(mr, rr.max(-1)[0]) and torch.equal(mar, rr.max(-1)[0].max(-1)[0])
+    ll = torch.randn(S * B)
+    rew = torch.randn(S * B)
+    bl = O.shared_baseline(rew, S)
+    assert bl.shape == (B, 1)

@@ -1,0 +1,69 @@
+"""CPU, build container only: re-run the LIVE reference (unmodified files from /root/reference
+through oracle/ref_standin.py) against oracle/am_rollout_oracle.py on fresh seeds.
+Skipped where /root/reference does not exist (the GPU box)."""
+
+import pytest
+import torch
+
+from oracle import am_rollout_oracle as O
+from oracle import ref_standin
+
+pytestmark = pytest.mark.skipif(not ref_standin.reference_available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_standin.load()
+
+
+@pytest.mark.parametrize("name,n", [("tsp", 20), ("cvrp", 20), ("tsp", 37), ("cvrp", 33)])
+@pytest.mark.parametrize("decode_type", ["greedy", "sampling", "multistart_greedy", "multistart_sampling"])
+def test_policy_forward_matches_reference(ref, name, n, decode_type):
+    torch.manual_seed(1000 + n)
+    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    env = Env(generator_params=dict(num_loc=n), check_solution=True)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=2).eval()
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    td0 = env.generator(batch_size=[6])
+    inst = {k: td0[k].clone() for k in td0.keys()}
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        torch.manual_seed(5)
+        out = pol(td.clone(), env, phase="test", decode_type=decode_type)
+        torch.manual_seed(5)
+        o = O.policy_forward(W, name, inst, decode_type=decode_type, num_layers=2)
+    assert torch.equal(out["actions"], o["actions"])
+    torch.testing.assert_close(out["reward"], o["reward"], rtol=1e-6, atol=0)
+    torch.testing.assert_close(out["log_likelihood"], o["log_likelihood"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tsp", "cvrp"])
+def test_multinomial_is_argmax_p_over_exp_noise(ref, name):
+    """The recorded-noise protocol used for sampling parity: torch.multinomial(p,1) consumes
+    exactly one empty_like(p).exponential_(1) draw per step."""
+    torch.manual_seed(3)
+    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    env = Env(generator_params=dict(num_loc=20), check_solution=True)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    td0 = env.generator(batch_size=[32])
+    inst = {k: td0[k].clone() for k in td0.keys()}
+    with torch.inference_mode():
+        torch.manual_seed(7)
+        out = pol(env.reset(td0.clone()), env, phase="train", decode_type="sampling")
+        torch.manual_seed(7)
+        o = O.policy_forward(W, name, inst, decode_type="sampling", num_layers=1,
+                             noise=lambda t, shape: torch.empty(shape).exponential_(1))
+    assert torch.equal(out["actions"], o["actions"])
+
+
+def test_generator_matches_reference(ref):
+    for name, n in (("tsp", 50), ("cvrp", 50), ("cvrp", 100)):
+        Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+        env = Env(generator_params=dict(num_loc=n))
+        torch.manual_seed(1234)
+        td = env.generator(batch_size=[5])
+        torch.manual_seed(1234)
+        inst = O.generate_instances(name, 5, n)
+        for k in inst:
+            assert torch.equal(td[k], inst[k]), (name, k)
