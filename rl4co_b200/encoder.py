@@ -1,0 +1,127 @@
+"""Attention-model graph encoder ("next" row): stock PyTorch modules
+with the reference's module tree so that a reference ``state_dict`` loads unchanged.
+
+  AttentionModelEncoder   rl4co/models/zoo/am/encoder.py:12-87
+  TSP/VRPInitEmbedding    rl4co/models/nn/env_embeddings/init.py:55-68,115-136
+  GraphAttentionNetwork   rl4co/models/nn/graph/attnnet.py:16-106
+  MultiHeadAttention      rl4co/models/nn/attention.py:64-134
+  Normalization           rl4co/models/nn/ops.py:30-54
+  MLP                     rl4co/models/nn/mlp.py:8-60
+
+It runs once per instance (dense [B*N,128] GEMMs + NxN attention through cuBLAS / SDPA); the
+per-node-selection loop it feeds is the hand-written part of this package.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class TSPInitEmbedding(nn.Module):
+    def __init__(self, embed_dim, linear_bias=True):
+        super().__init__()
+        self.init_embed = nn.Linear(2, embed_dim, linear_bias)
+
+    def forward(self, td):
+        return self.init_embed(td["locs"])
+
+
+class VRPInitEmbedding(nn.Module):
+    def __init__(self, embed_dim, linear_bias=True, node_dim: int = 3):
+        super().__init__()
+        self.init_embed = nn.Linear(node_dim, embed_dim, linear_bias)
+        self.init_embed_depot = nn.Linear(2, embed_dim, linear_bias)
+
+    def forward(self, td):
+        depot, cities = td["locs"][:, :1, :], td["locs"][:, 1:, :]
+        depot_embedding = self.init_embed_depot(depot)
+        node_embeddings = self.init_embed(torch.cat((cities, td["demand"][..., None]), -1))
+        return torch.cat((depot_embedding, node_embeddings), -2)
+
+
+class SkipConnection(nn.Module):
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x):
+        return x + self.module(x)
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, embed_dim: int, num_heads: int, bias: bool = True):
+        super().__init__()
+        self.num_heads = num_heads
+        self.Wqkv = nn.Linear(embed_dim, 3 * embed_dim, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+    def forward(self, x):
+        B, N, _ = x.shape
+        q, k, v = self.Wqkv(x).view(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+        out = F.scaled_dot_product_attention(q, k, v)
+        return self.out_proj(out.transpose(1, 2).reshape(B, N, -1))
+
+
+class Normalization(nn.Module):
+    def __init__(self, embed_dim, normalization="batch"):
+        super().__init__()
+        cls = {"batch": nn.BatchNorm1d, "instance": nn.InstanceNorm1d}[normalization]
+        self.normalizer = cls(embed_dim, affine=True)
+
+    def forward(self, x):
+        if isinstance(self.normalizer, nn.BatchNorm1d):
+            return self.normalizer(x.reshape(-1, x.size(-1))).view(*x.size())
+        return self.normalizer(x.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim: int, output_dim: int, num_neurons: list[int]):
+        super().__init__()
+        dims_in = [input_dim] + num_neurons
+        dims_out = num_neurons + [output_dim]
+        self.lins = nn.ModuleList(nn.Linear(i, o) for i, o in zip(dims_in, dims_out))
+
+    def forward(self, xs):
+        for lin in self.lins[:-1]:
+            xs = F.relu(lin(xs))
+        return self.lins[-1](xs)
+
+
+class MultiHeadAttentionLayer(nn.Sequential):
+    def __init__(self, embed_dim, num_heads=8, feedforward_hidden=512, normalization="batch"):
+        super().__init__(
+            SkipConnection(MultiHeadAttention(embed_dim, num_heads)),
+            Normalization(embed_dim, normalization),
+            SkipConnection(MLP(embed_dim, embed_dim, [feedforward_hidden] if feedforward_hidden > 0 else [])),
+            Normalization(embed_dim, normalization),
+        )
+
+
+class GraphAttentionNetwork(nn.Module):
+    def __init__(self, num_heads, embed_dim, num_layers, normalization="batch", feedforward_hidden=512):
+        super().__init__()
+        self.layers = nn.Sequential(*(MultiHeadAttentionLayer(embed_dim, num_heads, feedforward_hidden, normalization)
+                                      for _ in range(num_layers)))
+
+    def forward(self, x, mask=None):
+        assert mask is None, "Mask not yet supported!"
+        return self.layers(x)
+
+
+class AttentionModelEncoder(nn.Module):
+    def __init__(self, embed_dim: int = 128, init_embedding=None, env_name: str = "tsp", num_heads: int = 8,
+                 num_layers: int = 3, normalization: str = "batch", feedforward_hidden: int = 512, net=None, **_):
+        super().__init__()
+        env_name = getattr(env_name, "name", env_name)
+        self.env_name = env_name
+        if init_embedding is None:
+            init_embedding = {"tsp": TSPInitEmbedding, "cvrp": VRPInitEmbedding}[env_name](embed_dim)
+        self.init_embedding = init_embedding
+        self.net = GraphAttentionNetwork(num_heads, embed_dim, num_layers, normalization, feedforward_hidden) \
+            if net is None else net
+
+    def forward(self, td, mask=None):
+        init_h = self.init_embedding(td)
+        return self.net(init_h, mask), init_h

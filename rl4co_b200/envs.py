@@ -1,0 +1,307 @@
+"""Drop-in TSP / CVRP environments whose step / mask / reward run as CUDA kernels.
+
+Same plugin surface as rl4co's envs:
+  RL4COEnvBase   rl4co/envs/common/base.py:19-333  (reset / step / get_reward / get_action_mask /
+                 get_num_starts / select_start_nodes / check_solution_validity / generator / dataset)
+  TSPEnv         rl4co/envs/routing/tsp/env.py:22-192
+  CVRPEnv        rl4co/envs/routing/cvrp/env.py:22-256
+TensorDict keys, dtypes and shapes are exactly the reference's, so the reference's context
+embeddings / decoding strategies / REINFORCE loops can consume the state unchanged.
+
+`reset` only allocates state (torch, any device).  `step`, `get_action_mask`, `get_reward`
+and `check_solution_validity` call libcorollout and therefore require CUDA tensors: there
+is deliberately no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import native
+from .ops import get_num_starts, select_start_nodes
+from .tensordict import TensorDict
+
+# rl4co/envs/routing/cvrp/generator.py:15-30
+CAPACITIES = {10: 20.0, 15: 25.0, 20: 30.0, 30: 33.0, 40: 37.0, 50: 40.0, 60: 43.0, 75: 45.0,
+              100: 50.0, 125: 55.0, 150: 60.0, 200: 70.0, 500: 100.0, 1000: 150.0}
+
+
+class Generator:
+    """rl4co/envs/common/utils.py:19-32"""
+
+    def __call__(self, batch_size) -> TensorDict:
+        batch_size = [batch_size] if isinstance(batch_size, int) else list(batch_size)
+        return self._generate(batch_size)
+
+
+class TSPGenerator(Generator):
+    """rl4co/envs/routing/tsp/generator.py:14-58 (uniform locations)."""
+
+    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, **_):
+        self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
+
+    def _generate(self, batch_size) -> TensorDict:
+        locs = torch.rand(*batch_size, self.num_loc, 2) * (self.max_loc - self.min_loc) + self.min_loc
+        return TensorDict({"locs": locs}, batch_size=batch_size)
+
+
+class CVRPGenerator(Generator):
+    """rl4co/envs/routing/cvrp/generator.py:33-140 (uniform locations, integer demands 1..9
+    over the Kool et al. capacity table, depot = first sampled point)."""
+
+    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, min_demand: int = 1,
+                 max_demand: int = 10, vehicle_capacity: float = 1.0, capacity: float | None = None, **_):
+        self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
+        self.min_demand, self.max_demand = min_demand, max_demand
+        self.vehicle_capacity = vehicle_capacity
+        if capacity is None:
+            capacity = CAPACITIES.get(num_loc, None)
+        if capacity is None:
+            capacity = CAPACITIES[min(CAPACITIES.keys(), key=lambda x: abs(x - num_loc))]
+        self.capacity = capacity
+
+    def _generate(self, batch_size) -> TensorDict:
+        locs = torch.rand(*batch_size, self.num_loc + 1, 2) * (self.max_loc - self.min_loc) + self.min_loc
+        lo, hi = self.min_demand - 1, self.max_demand - 1
+        demand = torch.rand(*batch_size, self.num_loc) * (hi - lo) + lo
+        demand = (demand.int() + 1).float()
+        return TensorDict(
+            {"locs": locs[..., 1:, :], "depot": locs[..., 0, :], "demand": demand / self.capacity,
+             "capacity": torch.full((*batch_size, 1), self.capacity)},
+            batch_size=batch_size,
+        )
+
+
+class FusedEnvBase:
+    """Host-side mirror of RL4COEnvBase (rl4co/envs/common/base.py:19-333)."""
+
+    name = "base"
+    batch_locked = False
+
+    def __init__(self, *, check_solution: bool = True, seed: int | None = None, device: str = "cpu",
+                 batch_size=None, inplace: bool = False, **kwargs):
+        kwargs.pop("name", None)
+        self.check_solution = check_solution
+        self.device = torch.device(device)
+        self.batch_size = torch.Size([]) if batch_size is None else torch.Size(batch_size)
+        self.inplace = inplace  # update mask / visited buffers in place instead of allocating per step
+        if seed is None:
+            seed = torch.empty((), dtype=torch.int64).random_().item()
+        self.set_seed(seed)
+
+    # -- torchrl-ish bookkeeping -------------------------------------------------
+    def set_seed(self, seed):
+        self.rng = torch.manual_seed(seed)
+        return seed
+
+    def to(self, device):
+        if device is not None:
+            self.device = torch.device(device)
+        return self
+
+    # -- public API ---------------------------------------------------------------
+    def step(self, td: TensorDict) -> dict:
+        """rl4co/envs/common/base.py:121-133 (fast path: {"next": td})"""
+        return {"next": self._step(td)}
+
+    def reset(self, td: TensorDict | None = None, batch_size=None) -> TensorDict:
+        """rl4co/envs/common/base.py:135-143 (+ torchrl's done/terminated fill)"""
+        if batch_size is None:
+            batch_size = self.batch_size if td is None else td.batch_size
+        if td is None or td.is_empty():
+            td = self.generator(batch_size=batch_size)
+        batch_size = [batch_size] if isinstance(batch_size, int) else batch_size
+        self.to(td.device)
+        out = self._reset(td, batch_size=batch_size)
+        for key in ("done", "terminated"):
+            if key not in out.keys():
+                out.set(key, torch.zeros((*batch_size, 1), dtype=torch.bool, device=td.device))
+        return out
+
+    def get_reward(self, td: TensorDict, actions: torch.Tensor, check_solution: bool | None = None) -> torch.Tensor:
+        """rl4co/envs/common/base.py:180-190"""
+        check_solution = self.check_solution if check_solution is None else check_solution
+        if check_solution:
+            self.check_solution_validity(td, actions)
+        return self._get_reward(td, actions)
+
+    def get_num_starts(self, td):
+        return get_num_starts(td, self.name)
+
+    def select_start_nodes(self, td, num_starts):
+        return select_start_nodes(td, self, num_starts)
+
+    def dataset(self, batch_size=[], phase="train", filename=None):
+        """rl4co/envs/common/base.py:234-268 (generated data or .npz file)."""
+        from .data import TensorDictDataset
+
+        td = self.generator(batch_size) if filename is None else self.load_data(filename, batch_size)
+        return TensorDictDataset(td)
+
+    @staticmethod
+    def load_data(fpath, batch_size=[]):
+        from .data import load_npz_to_tensordict
+
+        return load_npz_to_tensordict(fpath)
+
+
+class FusedTSPEnv(FusedEnvBase):
+    """CUDA drop-in for rl4co.envs.TSPEnv (rl4co/envs/routing/tsp/env.py:22-192)."""
+
+    name = "tsp"
+
+    def __init__(self, generator: TSPGenerator | None = None, generator_params: dict = {}, **kwargs):
+        super().__init__(**kwargs)
+        self.generator = TSPGenerator(**generator_params) if generator is None else generator
+
+    def _reset(self, td: TensorDict, batch_size=None) -> TensorDict:
+        """tsp/env.py:88-113"""
+        device = td.device
+        init_locs = td["locs"]
+        num_loc = init_locs.shape[-2]
+        current_node = torch.zeros((*batch_size,), dtype=torch.int64, device=device)
+        available = torch.ones((*batch_size, num_loc), dtype=torch.bool, device=device)
+        i = torch.zeros((*batch_size, 1), dtype=torch.int64, device=device)
+        return TensorDict(
+            {
+                "locs": init_locs,
+                "first_node": current_node,
+                "current_node": current_node,
+                "i": i,
+                "action_mask": available,
+                "reward": torch.zeros((*batch_size, 1), dtype=torch.float32, device=device),
+            },
+            batch_size=batch_size,
+        )
+
+    def _step(self, td: TensorDict) -> TensorDict:
+        """tsp/env.py:60-86 in one kernel (co_tsp_step).  `first_node` follows the reference's
+        "set on the first step" rule per instance (the reference tests `td["i"].all() == 0`
+        batch-wide; identical whenever the batch advances in lock-step)."""
+        action = td["action"].contiguous()
+        mask_in = td["action_mask"]
+        if not mask_in.is_contiguous():
+            mask_in = mask_in.contiguous()
+        B = action.shape[0]
+        mask_out = mask_in if self.inplace else torch.empty_like(mask_in)
+        # fresh int64 state tensors (the reference rebinds, never mutates, these keys)
+        first_node = td["first_node"].clone()
+        current_node = torch.empty_like(action)
+        i = td["i"].clone()
+        done = torch.empty(B, dtype=torch.bool, device=action.device)
+        native.tsp_step(action, mask_in, mask_out, first_node, current_node, i.view(-1), done)
+        td.update(
+            {
+                "first_node": first_node,
+                "current_node": current_node,
+                "i": i,
+                "action_mask": mask_out,
+                "reward": torch.zeros_like(done),  # bool zeros, as in the reference (tsp/env.py:74)
+                "done": done,
+            }
+        )
+        return td
+
+    def _get_reward(self, td: TensorDict, actions: torch.Tensor) -> torch.Tensor:
+        """tsp/env.py:150-156"""
+        if self.check_solution:
+            self.check_solution_validity(td, actions)
+        return native.tour_length(td["locs"].contiguous(), actions.contiguous(), with_depot=False)
+
+    @staticmethod
+    def check_solution_validity(td: TensorDict, actions: torch.Tensor) -> None:
+        """tsp/env.py:158-164"""
+        bad = native.check_tours(actions.contiguous(), td["locs"].shape[-2])
+        assert bad == 0, "Invalid tour"
+
+
+class FusedCVRPEnv(FusedEnvBase):
+    """CUDA drop-in for rl4co.envs.CVRPEnv (rl4co/envs/routing/cvrp/env.py:22-256)."""
+
+    name = "cvrp"
+
+    def __init__(self, generator: CVRPGenerator | None = None, generator_params: dict = {}, **kwargs):
+        super().__init__(**kwargs)
+        self.generator = CVRPGenerator(**generator_params) if generator is None else generator
+
+    def _reset(self, td: TensorDict, batch_size=None) -> TensorDict:
+        """cvrp/env.py:98-124"""
+        device = td.device
+        td_reset = TensorDict(
+            {
+                "locs": torch.cat((td["depot"][:, None, :], td["locs"]), -2),
+                "demand": td["demand"],
+                "current_node": torch.zeros(*batch_size, 1, dtype=torch.long, device=device),
+                "used_capacity": torch.zeros((*batch_size, 1), device=device),
+                "vehicle_capacity": torch.full((*batch_size, 1), self.generator.vehicle_capacity, device=device),
+                "visited": torch.zeros((*batch_size, td["locs"].shape[-2] + 1), dtype=torch.uint8, device=device),
+            },
+            batch_size=batch_size,
+        )
+        td_reset.set("action_mask", self.get_action_mask(td_reset))
+        return td_reset
+
+    def _step(self, td: TensorDict) -> TensorDict:
+        """cvrp/env.py:66-96 incl. the trailing get_action_mask, one kernel (co_cvrp_step)."""
+        action = td["action"].contiguous()
+        B = action.shape[0]
+        visited_in = td["visited"].contiguous()
+        used_in = td["used_capacity"].contiguous()
+        visited_out = visited_in if self.inplace else torch.empty_like(visited_in)
+        used_out = torch.empty_like(used_in)
+        current_node = torch.empty(B, 1, dtype=torch.int64, device=action.device)
+        done = torch.empty(B, dtype=torch.bool, device=action.device)
+        mask_out = torch.empty(B, visited_in.shape[-1], dtype=torch.bool, device=action.device)
+        native.cvrp_step(action, td["demand"].contiguous(), td["vehicle_capacity"].contiguous(), used_in, used_out,
+                         visited_in, visited_out, current_node, done, mask_out)
+        td.update(
+            {
+                "current_node": current_node,
+                "used_capacity": used_out,
+                "visited": visited_out,
+                "reward": torch.zeros_like(done),
+                "done": done,
+            }
+        )
+        td.set("action_mask", mask_out)
+        return td
+
+    @staticmethod
+    def get_action_mask(td: TensorDict) -> torch.Tensor:
+        """cvrp/env.py:126-136 (co_cvrp_action_mask)"""
+        visited = td["visited"].contiguous()
+        mask = torch.empty(visited.shape, dtype=torch.bool, device=visited.device)
+        native.cvrp_action_mask(td["demand"].contiguous(), td["used_capacity"].contiguous(),
+                                td["vehicle_capacity"].contiguous(), visited,
+                                td["current_node"].contiguous(), mask)
+        return mask
+
+    def _get_reward(self, td: TensorDict, actions: torch.Tensor) -> torch.Tensor:
+        """cvrp/env.py:138-147"""
+        return native.tour_length(td["locs"].contiguous(), actions.contiguous(), with_depot=True)
+
+    @staticmethod
+    def check_solution_validity(td: TensorDict, actions: torch.Tensor) -> None:
+        """cvrp/env.py:149-177"""
+        bad = native.check_tours(actions.contiguous(), td["locs"].shape[-2], td["demand"].contiguous(),
+                                 td["vehicle_capacity"].contiguous().view(-1), B_inst=td["demand"].shape[0])
+        assert bad == 0, "Invalid tour"
+
+    @staticmethod
+    def load_data(fpath, batch_size=[]):
+        """cvrp/env.py:179-186: normalise demand by capacity."""
+        from .data import load_npz_to_tensordict
+
+        td_load = load_npz_to_tensordict(fpath)
+        td_load.set("demand", td_load["demand"] / td_load["capacity"][:, None])
+        return td_load
+
+
+ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv}
+
+
+def get_env(env_name: str, *args, **kwargs) -> FusedEnvBase:
+    """rl4co/envs/__init__.py get_env for the two envs on the path."""
+    if env_name not in ENV_REGISTRY:
+        raise ValueError(f"Unknown environment {env_name}. Available: {list(ENV_REGISTRY)}")
+    return ENV_REGISTRY[env_name](*args, **kwargs)

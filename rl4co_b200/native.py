@@ -1,0 +1,288 @@
+"""ctypes binding of libcorollout.so (C ABI in include/corollout.h).
+
+This is the *only* compute backend of the package: there is no CPU or PyTorch fallback.
+Every wrapper raises if the shared library is missing or a tensor is not a contiguous CUDA
+tensor of the exact dtype the ABI declares.  torch is used for device memory and streams
+only (``tensor.data_ptr()``, ``torch.cuda.current_stream().cuda_stream``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+LIB_PATH = os.path.join(_HERE, "libcorollout.so")
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu"]
+
+CO_OK = 0
+ENV_TSP, ENV_CVRP = 0, 1
+ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP}
+SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
+ROLLOUT_FORCED_START = 1
+EMBED_DIM, NUM_HEADS = 128, 8
+
+EXPORTS = [
+    "co_version", "co_last_error_string", "co_device_sm_count", "co_tsp_step", "co_cvrp_action_mask",
+    "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
+    "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats",
+]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class DecoderWeights(Structure):
+    _fields_ = [("project_context_t", c_void_p), ("w_placeholder", c_void_p), ("project_out_t", c_void_p)]
+
+
+class RolloutArgs(Structure):
+    _fields_ = [
+        ("env_kind", c_int32), ("select_mode", c_int32), ("B_inst", c_int32), ("num_starts", c_int32),
+        ("N", c_int32), ("T_max", c_int32), ("num_loc", c_int32), ("flags", c_int32),
+        ("tanh_clipping", c_float), ("temperature", c_float),
+        ("cache", c_void_p), ("graph_ctx", c_void_p), ("q_placeholder", c_void_p), ("w_capacity", c_void_p),
+        ("locs", c_void_p), ("demand", c_void_p), ("vehicle_capacity", c_void_p),
+        ("forced_actions", c_void_p), ("noise", c_void_p), ("seed", c_uint64), ("offset", c_uint64),
+        ("actions_out", c_void_p), ("logp_out", c_void_p), ("reward_out", c_void_p), ("loglik_out", c_void_p),
+        ("steps_out", c_void_p), ("max_steps_out", c_void_p), ("used_capacity_out", c_void_p),
+    ]
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libcorollout.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "co_common.cuh"),
+                                                      os.path.join(INCLUDE, "corollout.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU/PyTorch fallback for the rollout path)")
+    L = ctypes.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
+    L.co_last_error_string.restype = c_char_p
+    L.co_rollout.argtypes = [POINTER(RolloutArgs), c_void_p]
+    L.co_pointer_logits.argtypes = [c_int, POINTER(DecoderWeights)] + [c_void_p] * 12 + [c_int, c_int, c_int, c_int, c_void_p]
+    L.co_select_action.argtypes = [c_void_p] * 6 + [c_int, c_float, c_float, c_int, c_uint64, c_uint64, c_int, c_int, c_void_p]
+    L.co_tsp_step.argtypes = [c_void_p] * 7 + [c_int, c_int, c_void_p]
+    L.co_cvrp_action_mask.argtypes = [c_void_p] * 6 + [c_int, c_int, c_void_p]
+    L.co_cvrp_step.argtypes = [c_void_p] * 10 + [c_int, c_int, c_void_p]
+    L.co_tour_length.argtypes = [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
+    L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
+    L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.co_cache_width.argtypes = [c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != CO_OK:
+        msg = lib().co_last_error_string().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed with code {rc}: {msg}")
+
+
+def _ptr(t: torch.Tensor | None, dtype: torch.dtype | None = None, name: str = "tensor", strided: bool = False):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise NativeLibraryError(f"{name}: libcorollout needs CUDA tensors (got device {t.device}); "
+                                 "there is no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not strided and not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+F32, I64, U8, I32 = torch.float32, torch.int64, torch.uint8, torch.int32
+
+
+def _bool_ptr(t, name):
+    """bool tensors are 1 byte; accept bool or uint8."""
+    if t is None:
+        return None
+    if t.dtype not in (torch.bool, torch.uint8):
+        raise TypeError(f"{name}: expected bool/uint8, got {t.dtype}")
+    return _ptr(t, None, name)
+
+
+# ----------------------------------------------------------------------------- wrappers
+
+
+def version() -> int:
+    return lib().co_version()
+
+
+def cache_width(env_name: str) -> int:
+    return lib().co_cache_width(ENV_KIND[env_name])
+
+
+def rollout_max_nodes() -> int:
+    return lib().co_rollout_max_nodes()
+
+
+def tsp_step(action, mask_in, mask_out, first_node, current_node, i, done):
+    B, N = mask_in.shape
+    _check(lib().co_tsp_step(_ptr(action, I64, "action"), _bool_ptr(mask_in, "mask_in"), _bool_ptr(mask_out, "mask_out"),
+                             _ptr(first_node, I64, "first_node"), _ptr(current_node, I64, "current_node"),
+                             _ptr(i, I64, "i"), _bool_ptr(done, "done"), B, N, _stream()), "co_tsp_step")
+
+
+def cvrp_action_mask(demand, used, cap, visited, current_node, mask_out):
+    B, N = visited.shape
+    _check(lib().co_cvrp_action_mask(_ptr(demand, F32, "demand"), _ptr(used, F32, "used"), _ptr(cap, F32, "cap"),
+                                     _ptr(visited, U8, "visited"), _ptr(current_node, I64, "current_node"),
+                                     _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_cvrp_action_mask")
+
+
+def cvrp_step(action, demand, cap, used_in, used_out, visited_in, visited_out, current_node, done, mask_out):
+    B, N = visited_in.shape
+    _check(lib().co_cvrp_step(_ptr(action, I64, "action"), _ptr(demand, F32, "demand"), _ptr(cap, F32, "cap"),
+                              _ptr(used_in, F32, "used_in"), _ptr(used_out, F32, "used_out"),
+                              _ptr(visited_in, U8, "visited_in"), _ptr(visited_out, U8, "visited_out"),
+                              _ptr(current_node, I64, "current_node"), _bool_ptr(done, "done"),
+                              _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_cvrp_step")
+
+
+def tour_length(locs, actions, with_depot: bool):
+    B, T = actions.shape
+    B_locs, N = locs.shape[0], locs.shape[1]
+    reward = torch.empty(B, dtype=F32, device=actions.device)
+    _check(lib().co_tour_length(_ptr(locs, F32, "locs"), _ptr(actions, I64, "actions"), _ptr(reward, F32, "reward"),
+                                B, B_locs, N, T, int(with_depot), _stream()), "co_tour_length")
+    return reward
+
+
+def check_tours(actions, N, demand=None, cap=None, B_inst=None) -> int:
+    """Number of invalid tours (one host sync, like the reference's asserts)."""
+    B, T = actions.shape
+    bad = torch.zeros(1, dtype=I32, device=actions.device)
+    _check(lib().co_check_tours(_ptr(actions, I64, "actions"), _ptr(demand, F32, "demand"), _ptr(cap, F32, "cap"),
+                                _ptr(bad, I32, "bad"), B, B if B_inst is None else B_inst, N, T, _stream()),
+           "co_check_tours")
+    return int(bad.item())
+
+
+def pointer_logits(env_name, weights: DecoderWeights, node_emb, graph_ctx, K, V, L, mask, first_node, current_node,
+                   i, used, cap, B_traj, B_inst, N):
+    """K / V / L: [B_inst, N, E] tensors, either contiguous or column-block views of one
+    [B_inst, N, W] cache (same row stride, unit channel stride)."""
+    ld = K.stride(1)
+    for name, x in (("glimpse_key", K), ("glimpse_val", V), ("logit_key", L)):
+        if x.stride(2) != 1 or x.stride(1) != ld or x.stride(0) != N * ld:
+            raise ValueError(f"{name}: unsupported strides {x.stride()}")
+    logits = torch.empty(B_traj, N, dtype=F32, device=node_emb.device)
+    _check(lib().co_pointer_logits(ENV_KIND[env_name], ctypes.byref(weights), _ptr(node_emb, F32, "node_emb"),
+                                   _ptr(graph_ctx, F32, "graph_ctx"), _ptr(K, F32, "glimpse_key", True),
+                                   _ptr(V, F32, "glimpse_val", True), _ptr(L, F32, "logit_key", True),
+                                   _bool_ptr(mask, "action_mask"), _ptr(first_node, I64, "first_node"),
+                                   _ptr(current_node, I64, "current_node"), _ptr(i, I64, "i"),
+                                   _ptr(used, F32, "used_capacity"), _ptr(cap, F32, "vehicle_capacity"),
+                                   _ptr(logits, F32, "logits"), B_traj, B_inst, N, ld, _stream()), "co_pointer_logits")
+    return logits
+
+
+def select_action(logits, mask, mode, noise=None, action=None, tanh_clipping=10.0, temperature=1.0,
+                  mask_logits=True, store_all_logp=False, seed=0, offset=0):
+    B, N = logits.shape
+    if action is None:
+        action = torch.empty(B, dtype=I64, device=logits.device)
+    logp = torch.empty(B, dtype=F32, device=logits.device)
+    all_lp = torch.empty(B, N, dtype=F32, device=logits.device) if store_all_logp else None
+    _check(lib().co_select_action(_ptr(logits, F32, "logits"), _bool_ptr(mask, "mask"), _ptr(noise, F32, "noise"),
+                                  _ptr(action, I64, "action"), _ptr(logp, F32, "logp"), _ptr(all_lp, F32, "logprobs"),
+                                  mode, float(tanh_clipping), float(temperature), int(mask_logits), seed, offset,
+                                  B, N, _stream()), "co_select_action")
+    return action, logp, all_lp
+
+
+def reward_stats(reward, out2):
+    _check(lib().co_reward_stats(_ptr(reward, F32, "reward"), _ptr(out2, torch.float64, "out2"), reward.numel(),
+                                 _stream()), "co_reward_stats")
+
+
+def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, locs, demand, vehicle_capacity,
+            B_inst, N, num_starts=1, forced_start=False, num_loc=0, T_max=None, forced_actions=None, noise=None,
+            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0):
+    """Launch the persistent rollout kernel; returns dict of device tensors (no host sync)."""
+    dev = cache.device
+    S = max(1, int(num_starts))
+    B_traj = B_inst * S
+    if T_max is None:
+        T_max = N if env_name == "tsp" else 2 * (N - 1)
+    actions = torch.empty(B_traj, T_max, dtype=I64, device=dev)
+    logp = torch.empty(B_traj, T_max, dtype=F32, device=dev)
+    reward = torch.empty(B_traj, dtype=F32, device=dev)
+    loglik = torch.empty(B_traj, dtype=F32, device=dev)
+    steps = torch.empty(B_traj, dtype=I32, device=dev)
+    max_steps = torch.zeros(1, dtype=I32, device=dev)
+    used_out = torch.empty(B_traj, dtype=F32, device=dev) if env_name == "cvrp" else None
+    a = RolloutArgs()
+    a.env_kind, a.select_mode, a.B_inst, a.num_starts = ENV_KIND[env_name], select_mode, B_inst, S
+    a.N, a.T_max, a.num_loc, a.flags = N, T_max, int(num_loc), (ROLLOUT_FORCED_START if forced_start else 0)
+    a.tanh_clipping, a.temperature = float(tanh_clipping), float(temperature)
+    a.cache = _ptr(cache, F32, "cache")
+    a.graph_ctx = _ptr(graph_ctx, F32, "graph_ctx")
+    a.q_placeholder = _ptr(q_placeholder, F32, "q_placeholder")
+    a.w_capacity = _ptr(w_capacity, F32, "w_capacity")
+    a.locs = _ptr(locs, F32, "locs")
+    a.demand = _ptr(demand, F32, "demand")
+    a.vehicle_capacity = _ptr(vehicle_capacity, F32, "vehicle_capacity")
+    a.forced_actions = _ptr(forced_actions, I64, "forced_actions")
+    a.noise = _ptr(noise, F32, "noise")
+    a.seed, a.offset = int(seed), int(offset)
+    a.actions_out, a.logp_out = _ptr(actions, I64, "actions"), _ptr(logp, F32, "logp")
+    a.reward_out, a.loglik_out = _ptr(reward, F32, "reward"), _ptr(loglik, F32, "loglik")
+    a.steps_out, a.max_steps_out = _ptr(steps, I32, "steps"), _ptr(max_steps, I32, "max_steps")
+    a.used_capacity_out = _ptr(used_out, F32, "used_out")
+    if cache.shape != (B_inst, N, cache_width(env_name)):
+        raise ValueError(f"cache shape {tuple(cache.shape)} != {(B_inst, N, cache_width(env_name))}")
+    if forced_actions is not None and tuple(forced_actions.shape) != (B_traj, T_max):
+        raise ValueError(f"forced_actions must be [{B_traj}, {T_max}], got {tuple(forced_actions.shape)}")
+    if noise is not None and (noise.dim() != 3 or noise.shape[1] != B_traj or noise.shape[2] != N):
+        raise ValueError(f"noise must be [T, {B_traj}, {N}], got {tuple(noise.shape)}")
+    _check(lib().co_rollout(ctypes.byref(a), _stream()), "co_rollout")
+    return {"actions": actions, "logprobs": logp, "reward": reward, "log_likelihood": loglik, "steps": steps,
+            "max_steps": max_steps, "used_capacity": used_out}
