@@ -122,6 +122,16 @@ class AttentionModelEncoder(nn.Module):
         self.net = GraphAttentionNetwork(num_heads, embed_dim, num_layers, normalization, feedforward_hidden) \
             if net is None else net
 
+    #: instances per forward chunk when no autograd graph is needed (bounds the FFN-hidden
+    #: activation to chunk * N * 512 floats; exact because eval-mode norms are per element)
+    inference_chunk = 8192
+
     def forward(self, td, mask=None):
         init_h = self.init_embedding(td)
-        return self.net(init_h, mask), init_h
+        B = init_h.shape[0]
+        if torch.is_grad_enabled() or self.training or B <= self.inference_chunk:
+            return self.net(init_h, mask), init_h
+        out = torch.empty_like(init_h)
+        for lo in range(0, B, self.inference_chunk):
+            out[lo:lo + self.inference_chunk] = self.net(init_h[lo:lo + self.inference_chunk], mask)
+        return out, init_h

@@ -318,9 +318,9 @@ def test_full_policy_vs_oracle_seeded(dev, env_name, n, batch, mode):
         out = pol(td, env, phase="test", decode_type=mode, return_sum_log_likelihood=False, **kw)
         st0 = O.env_reset(env_name, inst)
         h, _ = O.encoder_forward(W, env_name, st0, num_layers=2)
-    torch.testing.assert_close(pol.encoder(td)[0].cpu(), h, rtol=1e-4, atol=1e-4)
+        h_gpu = pol.encoder(td)[0].cpu()
+    torch.testing.assert_close(h_gpu, h, rtol=1e-4, atol=1e-4)
     # use the GPU encoder output for the prefix oracle so that decoder parity is isolated
-    h_gpu = pol.encoder(td)[0].detach().cpu()
     _check_against_prefix_oracle(W, env_name, inst, h_gpu, out, mode, noise=noise)
 
 
