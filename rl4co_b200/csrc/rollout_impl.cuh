@@ -1,0 +1,451 @@
+// Persistent whole-episode rollout kernel (the north-star kernel) -- implementation header,
+// instantiated per environment in rollout_tsp.cu / rollout_cvrp.cu.
+//
+// Replaces the `while not td["done"].all()` loop of ConstructivePolicy.forward
+// (rl4co/models/common/constructive/base.py:219-251): per node selection it fuses
+//   AttentionModelDecoder.forward      rl4co/models/zoo/am/decoder.py:156-193
+//     context embedding                nn/env_embeddings/context.py:61-74,116-134,147-149
+//     PointerAttention                 nn/attention.py:274-320
+//   DecodingStrategy.step              rl4co/utils/decoding.py:138-188,344-461
+//   TSPEnv._step / CVRPEnv._step       envs/routing/tsp/env.py:60-86, cvrp/env.py:66-136
+// and at the end get_reward (ops.py:82-90) and get_log_likelihood (decoding.py:38-62).
+//
+// Design (B200): one CTA (256 threads = 8 warps) owns one instance for its whole episode.
+//   * warp h holds head h of glimpse_key / glimpse_val for all nodes IN REGISTERS as float2
+//     pairs (lane l owns nodes l, l+32, ..) and uses Blackwell's packed FFMA2; the glimpse
+//     (scores -> masked softmax -> weighted value sum) is warp-local: one REDUX.MAX on an
+//     order-preserving integer key, one shuffle all-reduce, one shared-memory transpose;
+//   * logit_key is pre-multiplied by project_out on the host side of the cache
+//     (logits = heads . (L W_out)[n]) and also lives in registers: thread (node, part) owns
+//     16*SPL contiguous channels of its node;
+//   * the per-node context table (node_emb @ Wctx_cur^T) sits in shared memory, so the next
+//     query is one row read + the per-episode fixed part;
+//   * the log-softmax uses the tanh-clip bound as its fixed offset (z <= clip/T), so per-warp
+//     partial sums add up without any exp in the cross-warp combine; arg-max is REDUX.MAX +
+//     ballot; sampling is arg-max of z - log q (Gumbel form of torch.multinomial's p/q);
+//   * the visited set is a bitmask in registers (SPL x uint32) replicated in every thread;
+//     capacity / current node are replicated scalars; the CVRP depot rule uses a pointer into
+//     the demand-sorted customer list instead of a block-wide OR;
+//   * exactly two block barriers per node selection; no state in HBM.
+// HBM traffic per instance = one read of its cache rows + T*(8+4) B of outputs.
+#pragma once
+#include "co_common.cuh"
+
+namespace co {
+
+#define CO_MODE_GREEDY 0
+#define CO_MODE_SAMPLE 1
+#define CO_MODE_EVALUATE 2
+
+template <int SPL>
+struct Cfg {
+  static constexpr int NS = 32 * SPL;       // node slots
+  static constexpr int PARTS = 8 / SPL;     // threads sharing one node in the logits phase
+  static constexpr int NPW = 32 / PARTS;    // nodes per warp in the logits phase
+  static constexpr int EPP = 16 * SPL;      // channels of logit_key per thread
+  static constexpr int OPAD = EPP + 4;      // padded stride of a part's chunk in `o` (bank spread)
+  static constexpr int MINB = SPL == 4 ? 1 : (SPL == 2 ? 2 : 3);
+};
+
+constexpr int TILE_LD = 20;  // padded row of the per-warp AV transpose tile
+
+template <int SPL>
+struct Smem {
+  float ptab[(32 * SPL + 1) * E];   // current-node context table; last row = zeros
+  float qfix[E];                    // per-episode fixed part of the query
+  float wcap[E];                    // cvrp: remaining-capacity column of project_context
+  float o[8 * (16 * SPL + 4) + 8];  // concatenated heads (padded per part)
+  float tile[8][32 * TILE_LD];      // per-warp transpose tile for the value reduction
+  unsigned red_key[8];              // per-warp best key (order-preserving uint of a float)
+  int red_idx[8];                   // per-warp arg-max node
+  float red_sum[8];                 // per-warp sum exp(z - Zb)
+  float dem[32 * SPL];
+  float2 loc[32 * SPL];
+  unsigned char order[32 * SPL];    // cvrp: customers sorted by demand (ascending)
+  float ll_acc;
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// order-preserving float -> uint (so REDUX.MAX on integers is an exact float max)
+__device__ __forceinline__ unsigned fkey(float f) {
+  unsigned u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+template <int ENV>
+__device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used, float thr, int cur, bool anyfeas) {
+  if (ENV == CO_ENV_TSP) return !visbit;
+  // cvrp/env.py:126-136
+  if (n == 0) return !(cur == 0 && anyfeas);
+  return !visbit && !((d + used) > thr);
+}
+
+template <int SPL, int ENV, int MODE>
+__global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_rollout_args A) {
+  using C = Cfg<SPL>;
+  constexpr int NS = C::NS, PARTS = C::PARTS, NPW = C::NPW, EPP = C::EPP, OPAD = C::OPAD;
+  constexpr int CW = (ENV == CO_ENV_TSP ? 5 : 4) * E;   // cache row width
+  constexpr int CUR_BLK = (ENV == CO_ENV_TSP ? 4 : 3);  // block holding the current-node table
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<SPL>& sm = *reinterpret_cast<Smem<SPL>*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+  const int N = A.N, B_inst = A.B_inst, S = A.num_starts, T_max = A.T_max;
+  const int B_traj = B_inst * S;
+  const bool forced_start = (S > 1) && (A.flags & CO_ROLLOUT_FORCED_START);
+  const bool philox = (A.noise == nullptr);
+  const int nL = h * NPW + lane / PARTS;  // node owned in the logits phase
+  const int part = lane % PARTS;
+  const float clip = A.tanh_clipping, inv_temp = 1.0f / A.temperature;
+  const float Zb = clip * inv_temp;       // z = clip*tanh(.)/T <= Zb: fixed log-softmax offset
+  float* tile = sm.tile[h];
+
+  float2 Kr[SPL][8], Vr[SPL][8], Lr[EPP / 2];
+
+  for (int b = blockIdx.x; b < B_inst; b += gridDim.x) {
+    __syncthreads();  // previous instance no longer reads shared memory
+    const float* crow = A.cache + (size_t)b * N * CW;
+    // ---- one HBM read of the instance: registers <- glimpse_key/val head slices, folded logit key
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+      const int n = lane + 32 * k;
+      if (n < N) {
+        const float4* ks = reinterpret_cast<const float4*>(crow + (size_t)n * CW + 0 * E + h * D);
+        const float4* vs = reinterpret_cast<const float4*>(crow + (size_t)n * CW + 1 * E + h * D);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 kv = __ldg(ks + c), vv = __ldg(vs + c);
+          Kr[k][2 * c] = make_float2(kv.x, kv.y); Kr[k][2 * c + 1] = make_float2(kv.z, kv.w);
+          Vr[k][2 * c] = make_float2(vv.x, vv.y); Vr[k][2 * c + 1] = make_float2(vv.z, vv.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { Kr[k][j] = make_float2(0.f, 0.f); Vr[k][j] = make_float2(0.f, 0.f); }
+      }
+    }
+    if (nL < N) {
+      const float4* ls = reinterpret_cast<const float4*>(crow + (size_t)nL * CW + 2 * E + part * EPP);
+#pragma unroll
+      for (int c = 0; c < EPP / 4; ++c) {
+        const float4 lv = __ldg(ls + c);
+        Lr[2 * c] = make_float2(lv.x, lv.y); Lr[2 * c + 1] = make_float2(lv.z, lv.w);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < EPP / 2; ++c) Lr[c] = make_float2(0.f, 0.f);
+    }
+    // ---- shared memory <- context table, coordinates, demands
+    for (int idx = tid; idx < N * (E / 4); idx += 256) {
+      const int n = idx >> 5, c = idx & 31;
+      reinterpret_cast<float4*>(sm.ptab + n * E)[c] =
+          __ldg(reinterpret_cast<const float4*>(crow + (size_t)n * CW + CUR_BLK * E) + c);
+    }
+    if (tid < E) {
+      sm.ptab[NS * E + tid] = 0.f;
+      sm.wcap[tid] = (ENV == CO_ENV_CVRP) ? A.w_capacity[tid] : 0.f;
+    }
+    if (tid < NS) {
+      sm.loc[tid] = (tid < N) ? reinterpret_cast<const float2*>(A.locs)[(size_t)b * N + tid] : make_float2(0.f, 0.f);
+      sm.dem[tid] = (ENV == CO_ENV_CVRP && tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
+    }
+    const float cap = (ENV == CO_ENV_CVRP && A.vehicle_capacity) ? A.vehicle_capacity[b] : 1.0f;
+    const float thr = cap + 1e-5f;  // fp32 add, as `td["vehicle_capacity"] + 1e-5`
+    __syncthreads();
+    if (ENV == CO_ENV_CVRP) {  // rank-sort customers by demand (ties by index) -> sm.order
+      if (tid >= 1 && tid < N) {
+        const float d = sm.dem[tid];
+        int rank = 0;
+        for (int m = 1; m < N; ++m) {
+          const float dm = sm.dem[m];
+          rank += (dm < d || (dm == d && m < tid)) ? 1 : 0;
+        }
+        sm.order[rank] = (unsigned char)tid;
+      }
+      __syncthreads();
+    }
+    float dmk[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) dmk[k] = sm.dem[lane + 32 * k];
+    const float dL = sm.dem[nL];
+
+    for (int s = 0; s < S; ++s) {
+      const int traj = s * B_inst + b;  // start-major, rl4co/utils/ops.py:10-29
+      int64_t* act_row = A.actions_out + (size_t)traj * T_max;
+      float* lp_row = A.logp_out + (size_t)traj * T_max;
+      // ---------------- reset (tsp/env.py:88-113, cvrp/env.py:98-124)
+      uint32_t vis[SPL];
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) {
+        const int lo = 32 * k;
+        vis[k] = (N >= lo + 32) ? 0u : (N <= lo ? 0xffffffffu : (0xffffffffu << (N - lo)));
+      }
+      int cur = (ENV == CO_ENV_TSP) ? NS : 0;  // NS -> zero row: step-0 placeholder context
+      int prev = 0, first = 0, t = 0, dstep = 0, optr = 0;
+      float used = 0.f, dist = 0.f;
+      bool anyfeas = false, done = false;
+      __syncthreads();  // previous trajectory finished with qfix / ll_acc
+      if (tid < E) {
+        float g = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;
+        if (ENV == CO_ENV_TSP && !forced_start) g += A.q_placeholder[tid];
+        sm.qfix[tid] = g;
+      }
+      if (tid == 0) sm.ll_acc = 0.f;
+
+      auto vis_bit = [&](int n) -> bool {  // select chain: no dynamic register indexing
+        uint32_t w = vis[0];
+#pragma unroll
+        for (int k = 1; k < SPL; ++k)
+          if ((n >> 5) == k) w = vis[k];
+        return (w >> (n & 31)) & 1u;
+      };
+      // one environment transition, replicated in every thread
+      auto env_step = [&](int a) {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k)
+          if ((a >> 5) == k) vis[k] |= 1u << (a & 31);
+        if (h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
+          const float2 pa = sm.loc[a], pp = sm.loc[prev];
+          const float dx = pa.x - pp.x, dy = pa.y - pp.y;
+          if (ENV == CO_ENV_CVRP || t != 0) dist += sqrtf(dx * dx + dy * dy);
+        }
+        if (ENV == CO_ENV_TSP) {
+          if (t == 0) first = a;
+        } else {
+          used = (used + sm.dem[a == 0 ? 1 : a]) * (a != 0 ? 1.0f : 0.0f);  // cvrp/env.py:70-76
+          // depot rule (cvrp/env.py:134): any unvisited customer that still fits <=> the
+          // unvisited customer of least demand fits (fp32 add is monotone in the demand)
+          const int ncust = N - 1;
+          while (optr < ncust && vis_bit(sm.order[optr])) ++optr;
+          anyfeas = (optr < ncust) && !((sm.dem[sm.order[optr < ncust ? optr : 0]] + used) > thr);
+        }
+        prev = a; cur = a; ++t;
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) all = all && (vis[k] == 0xffffffffu);
+        done = all;
+      };
+
+      if (forced_start) {  // multistart pre_decoder_hook, decoding.py:309-326 + ops.py:128-149
+        const int a0 = (s % A.num_loc) + (ENV == CO_ENV_CVRP ? 1 : 0);
+        if (tid == 0) { act_row[0] = a0; lp_row[0] = 0.f; }
+        env_step(a0);
+        if (ENV == CO_ENV_TSP && tid < E) sm.qfix[tid] += __ldg(crow + (size_t)a0 * CW + 3 * E + tid);
+      } else if (ENV == CO_ENV_CVRP) {
+        anyfeas = !((sm.dem[sm.order[0]] + used) > thr);
+      }
+      __syncthreads();
+
+      while (!done && t < T_max) {
+        // early, latency-tolerant loads for this step
+        int forced = 0;
+        float gum = 0.f;  // -log q, q ~ Exp(1): Gumbel perturbation for sampling
+        if (MODE == CO_MODE_EVALUATE) forced = (int)A.forced_actions[(size_t)traj * T_max + t];
+        if (MODE == CO_MODE_SAMPLE && part == 0 && nL < N) {
+          const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstep, nL)
+                                 : A.noise[((size_t)dstep * B_traj + traj) * N + nL];
+          gum = -logf(q);
+        }
+
+        // ---------------- glimpse: warp h = head h, fully warp-local
+        {
+          const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur * E + h * D);
+          const float4* qf = reinterpret_cast<const float4*>(sm.qfix + h * D);
+          const float4* wc = reinterpret_cast<const float4*>(sm.wcap + h * D);
+          const float rem = cap - used;  // context.py:147-149
+          float2 sc2[SPL];
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) sc2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 p = pr[c], f = qf[c];
+            float2 qa = make_float2(p.x + f.x, p.y + f.y), qb = make_float2(p.z + f.z, p.w + f.w);
+            if (ENV == CO_ENV_CVRP) {
+              const float4 w = wc[c];
+              qa = ffma2(make_float2(w.x, w.y), make_float2(rem, rem), qa);
+              qb = ffma2(make_float2(w.z, w.w), make_float2(rem, rem), qb);
+            }
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+              sc2[k] = ffma2(qa, Kr[k][2 * c], sc2[k]);
+              sc2[k] = ffma2(qb, Kr[k][2 * c + 1], sc2[k]);
+            }
+          }
+          // scores in log2 units: s * (1/sqrt(head_dim)) * log2(e)
+          float sc[SPL], m = -INFINITY;
+          bool fz[SPL];
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) {
+            fz[k] = feasible<ENV>(lane + 32 * k, (vis[k] >> lane) & 1u, dmk[k], used, thr, cur, anyfeas);
+            sc[k] = fz[k] ? (sc2[k].x + sc2[k].y) * (0.25f * LOG2E) : -INFINITY;
+            m = fmaxf(m, sc[k]);
+          }
+          m = funkey(__reduce_max_sync(FULL, fkey(m)));
+          float2 acc[8];
+          float esum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) {
+            const float e = fz[k] ? ex2(sc[k] - m) : 0.f;
+            esum += e;
+            const float2 e2 = make_float2(e, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = ffma2(e2, Vr[k][j], acc[j]);
+          }
+          // lane-sum of the 16 partial outputs through a padded shared-memory transpose
+          float4* trow = reinterpret_cast<float4*>(tile + lane * TILE_LD);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) trow[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
+          esum = warp_sum(esum);
+          __syncwarp();
+          const int d = lane & 15, half = lane >> 4;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; r += 4) {  // half 1 reads rows rotated by 4: bank-conflict free
+            s0 += tile[(16 * half + ((r + 0 + 4 * half) & 15)) * TILE_LD + d];
+            s1 += tile[(16 * half + ((r + 1 + 4 * half) & 15)) * TILE_LD + d];
+            s2 += tile[(16 * half + ((r + 2 + 4 * half) & 15)) * TILE_LD + d];
+            s3 += tile[(16 * half + ((r + 3 + 4 * half) & 15)) * TILE_LD + d];
+          }
+          float r = (s0 + s1) + (s2 + s3);
+          r += __shfl_xor_sync(FULL, r, 16);
+          if (lane < 16) {
+            const int e = h * D + d;
+            sm.o[e + 4 * (e / EPP)] = __fdividef(r, esum);
+          }
+        }
+        __syncthreads();  // B1: heads complete
+
+        // ---------------- pointer logits + tanh clip + mask: thread (nL, part)
+        const bool fzL = feasible<ENV>(nL, vis_bit(nL), dL, used, thr, cur, anyfeas);
+        float z;
+        {
+          const float4* ov = reinterpret_cast<const float4*>(sm.o + part * OPAD);
+          float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
+#pragma unroll
+          for (int c = 0; c < EPP / 4; c += 2) {
+            const float4 x = ov[c], y = ov[c + 1];
+            p0 = ffma2(make_float2(x.x, x.y), Lr[2 * c], p0);
+            p1 = ffma2(make_float2(x.z, x.w), Lr[2 * c + 1], p1);
+            p2 = ffma2(make_float2(y.x, y.y), Lr[2 * c + 2], p2);
+            p3 = ffma2(make_float2(y.z, y.w), Lr[2 * c + 3], p3);
+          }
+          float p = ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
+#pragma unroll
+          for (int off = PARTS / 2; off > 0; off >>= 1) p += __shfl_xor_sync(FULL, p, off);
+          const float lg = tanhf(p * 0.08838834764831845f) * clip;  // /sqrt(E), tanh clip (decoding.py:169-170)
+          z = fzL ? lg * inv_temp : -INFINITY;                       // mask, temperature (decoding.py:173-177)
+        }
+        {
+          const float ex = (part == 0) ? ex2((z - Zb) * LOG2E) : 0.f;  // exp(z - Zb) in (0,1]; 0 if masked
+          const float wsum = warp_sum(ex);
+          const float keyf = (MODE == CO_MODE_SAMPLE) ? ((part == 0) ? z + gum : -INFINITY) : z;
+          const unsigned key = fkey(keyf);
+          const unsigned wkey = __reduce_max_sync(FULL, key);
+          const unsigned vote = __ballot_sync(FULL, key == wkey);
+          if (lane == 0) {
+            sm.red_key[h] = wkey;
+            sm.red_idx[h] = h * NPW + (__ffs(vote) - 1) / PARTS;  // first lane wins ties = lowest node
+            sm.red_sum[h] = wsum;
+          }
+        }
+        __syncthreads();  // B2: per-warp partials complete
+        int a;
+        float Ssum;
+        {
+          const uint4 k0 = reinterpret_cast<const uint4*>(sm.red_key)[0], k1 = reinterpret_cast<const uint4*>(sm.red_key)[1];
+          const int4 i0 = reinterpret_cast<const int4*>(sm.red_idx)[0], i1 = reinterpret_cast<const int4*>(sm.red_idx)[1];
+          const float4 u0 = reinterpret_cast<const float4*>(sm.red_sum)[0], u1 = reinterpret_cast<const float4*>(sm.red_sum)[1];
+          Ssum = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
+          unsigned bk = k0.x; a = i0.x;  // strict '>' keeps the lowest warp (= lowest node) on ties
+          if (k0.y > bk) { bk = k0.y; a = i0.y; }
+          if (k0.z > bk) { bk = k0.z; a = i0.z; }
+          if (k0.w > bk) { bk = k0.w; a = i0.w; }
+          if (k1.x > bk) { bk = k1.x; a = i1.x; }
+          if (k1.y > bk) { bk = k1.y; a = i1.y; }
+          if (k1.z > bk) { bk = k1.z; a = i1.z; }
+          if (k1.w > bk) { bk = k1.w; a = i1.w; }
+        }
+        if (MODE == CO_MODE_EVALUATE) a = (forced < 0 || forced >= N) ? 0 : forced;
+        if (nL == a && part == 0) {  // log_softmax of the chosen node: (z - Zb) - log(sum exp(z - Zb))
+          const float lpL = (z - Zb) - lg2(Ssum) * LN2;
+          lp_row[t] = lpL;
+          sm.ll_acc += lpL;
+        }
+        if (tid == 0) act_row[t] = a;
+
+        // ---------------- environment step
+        const bool was_first = (ENV == CO_ENV_TSP) && (t == 0);
+        env_step(a);
+        ++dstep;
+        if (was_first) {  // context from now on: [h_first ; h_cur], context.py:129-133
+          if (tid < E) sm.qfix[tid] = (A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f) +
+                                      __ldg(crow + (size_t)a * CW + 3 * E + tid);
+          __syncthreads();
+        }
+      }
+
+      // ---------------- epilogue: reward, log-likelihood, padding
+      __syncthreads();
+      if (tid == 0) {
+        const float2 pa = sm.loc[(ENV == CO_ENV_TSP) ? first : 0], pp = sm.loc[prev];
+        const float dx = pa.x - pp.x, dy = pa.y - pp.y;
+        A.reward_out[traj] = -(dist + sqrtf(dx * dx + dy * dy));
+        A.loglik_out[traj] = sm.ll_acc;
+        if (A.steps_out) A.steps_out[traj] = t;
+        if (A.used_capacity_out) A.used_capacity_out[traj] = used;
+        if (A.max_steps_out) atomicMax(A.max_steps_out, t);
+      }
+      // done instances keep selecting the depot with log-prob 0 until the batch finishes
+      for (int c = t + tid; c < T_max; c += 256) { act_row[c] = 0; lp_row[c] = 0.f; }
+    }
+  }
+}
+
+template <int SPL, int ENV, int MODE>
+static int launch(const co_rollout_args& A, cudaStream_t st) {
+  auto kern = rollout_kernel<SPL, ENV, MODE>;
+  const size_t smem = sizeof(Smem<SPL>);
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_rollout: smem attribute: %s", cudaGetErrorString(e));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 256, smem);
+    if (e != cudaSuccess || ctas_per_sm < 1) return fail(CO_ERR_CUDA, "co_rollout: occupancy query failed%s");
+    configured = true;
+  }
+  int grid = device_info().sm_count * ctas_per_sm;
+  if (grid > A.B_inst) grid = A.B_inst;
+  kern<<<grid, 256, smem, st>>>(A);
+  return check_launch("co_rollout");
+}
+
+template <int ENV>
+static int dispatch(const co_rollout_args& A, cudaStream_t st) {
+  const int spl = A.N <= 32 ? 1 : (A.N <= 64 ? 2 : 4);
+  const int mode = A.select_mode == CO_SELECT_GREEDY ? CO_MODE_GREEDY
+                   : (A.select_mode == CO_SELECT_EVALUATE ? CO_MODE_EVALUATE : CO_MODE_SAMPLE);
+#define CO_CASE(S_, M_) if (spl == S_ && mode == M_) return launch<S_, ENV, M_>(A, st)
+  CO_CASE(1, CO_MODE_GREEDY); CO_CASE(2, CO_MODE_GREEDY); CO_CASE(4, CO_MODE_GREEDY);
+  CO_CASE(1, CO_MODE_SAMPLE); CO_CASE(2, CO_MODE_SAMPLE); CO_CASE(4, CO_MODE_SAMPLE);
+  CO_CASE(1, CO_MODE_EVALUATE); CO_CASE(2, CO_MODE_EVALUATE); CO_CASE(4, CO_MODE_EVALUATE);
+#undef CO_CASE
+  return fail(CO_ERR_BAD_ARG, "co_rollout: no kernel variant%s");
+}
+
+}  // namespace co

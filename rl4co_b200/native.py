@@ -20,7 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu"]
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu"]
+HEADERS = ["co_common.cuh", "rollout_impl.cuh"]
 
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
@@ -57,26 +58,42 @@ class RolloutArgs(Structure):
     ]
 
 
-def nvcc_command(out_path: str = LIB_PATH) -> list[str]:
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I", INCLUDE]
+
+
+def _nvcc() -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        nvcc = "nvcc"
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    return nvcc if os.path.exists(nvcc) else "nvcc"
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libcorollout.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "co_common.cuh"),
-                                                      os.path.join(INCLUDE, "corollout.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> str:
+    """Compile libcorollout.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+    Translation units are compiled in parallel, then linked."""
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(INCLUDE, "corollout.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
         return LIB_PATH
-    cmd = nvcc_command()
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + (extra_flags or []) + ["-c", os.path.join(CSRC, s), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, log = [], []
+    for s, obj, p in procs:
+        out, _ = p.communicate()
+        log.append(out)
+        if p.returncode != 0:
+            raise NativeLibraryError(f"nvcc failed on {s} ({p.returncode}):\n{out}")
+        objs.append(obj)
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise NativeLibraryError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+        raise NativeLibraryError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    build.last_log = "\n".join(log)
     return LIB_PATH
 
 
