@@ -134,10 +134,12 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def ncu_traffic():
+def ncu_traffic(batch):
+    """dram__bytes_read+write of the rollout kernel from the committed `ncu --set full` capture,
+    scaled per instance to this launch (the kernel streams each instance exactly once)."""
     try:
         with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f)["dram_bytes_per_instance"] * batch
     except Exception:
         return None
 
@@ -363,7 +365,7 @@ def run_ours(args):
     achieved = bytes_per_launch / (k_ms_avg * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "co::rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                "traffic": ncu_traffic(), "kernel_ms": k_ms_avg, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": ncu_traffic(B) if (env_name == "tsp" and n == 100) else None, "kernel_ms": k_ms_avg, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_share_of_step": k_ms_avg * args.steps / ms_total,
                 "note": "latency/issue-bound on-chip loop; HBM roofline shown as required, see DESIGN.md"}
 
