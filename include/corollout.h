@@ -191,6 +191,23 @@ int co_cache_width(int env_kind); /* floats per node row of the rollout cache */
 int co_rollout_max_nodes(void);
 int co_rollout(const co_rollout_args* args, void* stream);
 
+/* ------------------------------------------------------------------ dense projections
+ *
+ * fp32-accurate GEMM on tcgen05 tensor cores (kind::tf32, 3xTF32 hi/lo split, fp32 TMEM
+ * accumulators):  C[M,Nout] = epilogue(A[M,K] @ W[Nout,K]^T),
+ *   epilogue(v) = relu?((v + bias[n]) + residual[m,n]) * scale[n] + shift[n]   (each optional)
+ * Replaces the nn.Linear calls of AttentionModelDecoder._precompute_cache
+ * (rl4co/models/zoo/am/decoder.py:201-228) and of the AM encoder (nn/attention.py:110-134,
+ * nn/mlp.py:45-60; skip connection nn/ops.py:9-15 and eval-mode BatchNorm nn/ops.py:30-46 fold
+ * into residual / scale / shift).  W is passed pre-split (co_split_tf32): Whi = rna_tf32(W),
+ * Wlo = W - Whi.  Requirements: K % 32 == 0, Nout % 4 == 0, row strides (lda, ldc, ldr, in
+ * floats) % 4 == 0, 16-byte aligned pointers. */
+int co_split_tf32(const float* w, float* hi, float* lo, long n, void* stream);
+int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo, float* C,
+                   const float* bias, const float* residual, const float* scale,
+                   const float* shift, int M, int Nout, int K, int lda, int ldc, int ldr,
+                   int relu, void* stream);
+
 /* REINFORCE baseline statistics (rl4co/models/rl/reinforce/baselines.py:75-81):
  * out[0] += sum(reward), out[1] += count, in float64 so the cross-rank sum is
  * order-independent enough to reproduce the single-process mean. */

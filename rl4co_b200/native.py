@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu"]
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "gemm_tf32x3.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh"]
 
 CO_OK = 0
@@ -33,7 +33,7 @@ EMBED_DIM, NUM_HEADS = 128, 8
 EXPORTS = [
     "co_version", "co_last_error_string", "co_device_sm_count", "co_tsp_step", "co_cvrp_action_mask",
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
-    "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats",
+    "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3",
 ]
 
 
@@ -124,6 +124,8 @@ def lib() -> ctypes.CDLL:
     L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.co_cache_width.argtypes = [c_int]
+    L.co_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]
+    L.co_gemm_tf32x3.argtypes = [c_void_p] * 8 + [c_int] * 7 + [c_void_p]
     _lib = L
     return L
 
@@ -253,6 +255,33 @@ def select_action(logits, mask, mode, noise=None, action=None, tanh_clipping=10.
                                   mode, float(tanh_clipping), float(temperature), int(mask_logits), seed, offset,
                                   B, N, _stream()), "co_select_action")
     return action, logp, all_lp
+
+
+def split_tf32(w: torch.Tensor):
+    """(hi, lo) with hi = rna_tf32(w), lo = w - hi (both fp32) for co_gemm_tf32x3."""
+    w = w.detach().contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _check(lib().co_split_tf32(_ptr(w, F32, "w"), _ptr(hi, F32, "hi"), _ptr(lo, F32, "lo"), w.numel(), _stream()),
+           "co_split_tf32")
+    return hi, lo
+
+
+def gemm_tf32x3(a, w_hi, w_lo, out=None, bias=None, residual=None, scale=None, shift=None, relu=False):
+    """out[M, Nout] = epilogue(a[M, K] @ W[Nout, K]^T) on tcgen05 tensor cores (3xTF32).
+    `a`, `out`, `residual` may be row-strided 2-D views (unit column stride)."""
+    M, K = a.shape
+    Nout = w_hi.shape[0]
+    if out is None:
+        out = torch.empty(M, Nout, dtype=F32, device=a.device)
+    for name, x in (("a", a), ("out", out), ("residual", residual)):
+        if x is not None and (x.dim() != 2 or x.stride(1) != 1):
+            raise ValueError(f"{name}: need a 2-D tensor with unit column stride")
+    _check(lib().co_gemm_tf32x3(_ptr(a, F32, "a", True), _ptr(w_hi, F32, "w_hi"), _ptr(w_lo, F32, "w_lo"),
+                                _ptr(out, F32, "out", True), _ptr(bias, F32, "bias"), _ptr(residual, F32, "residual", True),
+                                _ptr(scale, F32, "scale"), _ptr(shift, F32, "shift"), M, Nout, K, a.stride(0),
+                                out.stride(0), residual.stride(0) if residual is not None else 0, int(relu), _stream()),
+           "co_gemm_tf32x3")
+    return out
 
 
 def reward_stats(reward, out2):
