@@ -100,7 +100,7 @@ class FusedAttentionModelDecoder(nn.Module):
     def __init__(self, embed_dim: int = 128, num_heads: int = 8, env_name: str = "tsp",
                  context_embedding=None, dynamic_embedding=None, mask_inner: bool = True,
                  out_bias_pointer_attn: bool = False, linear_bias: bool = False, use_graph_context: bool = True,
-                 check_nan: bool = True, sdpa_fn=None, pointer=None, moe_kwargs=None):
+                 check_nan: bool = True, sdpa_fn=None, pointer=None, moe_kwargs=None, cache_gemm: str = "tf32x3"):
         super().__init__()
         env_name = getattr(env_name, "name", env_name)
         if embed_dim != E or num_heads != native.NUM_HEADS:
@@ -120,6 +120,9 @@ class FusedAttentionModelDecoder(nn.Module):
         self.use_graph_context = use_graph_context
         self.check_nan = check_nan
         self.is_dynamic_embedding = False
+        #: "tf32x3": hand-written tcgen05 3xTF32 GEMM (fp32-class accuracy, inference / no-grad only);
+        #: "cublas": torch.nn.functional.linear (strict fp32 SIMT; always used when autograd is on)
+        self.cache_gemm = cache_gemm
 
     # ------------------------------------------------------------------ cache
     def fused_weight(self) -> torch.Tensor:
@@ -134,7 +137,14 @@ class FusedAttentionModelDecoder(nn.Module):
 
     def _precompute_cache(self, embeddings: torch.Tensor, num_starts: int = 0) -> FusedPrecomputedCache:
         """am/decoder.py:201-228"""
-        cache = torch.nn.functional.linear(embeddings, self.fused_weight())
+        wcat = self.fused_weight()
+        if self.cache_gemm == "tf32x3" and embeddings.is_cuda and not (torch.is_grad_enabled() and (
+                embeddings.requires_grad or wcat.requires_grad)):
+            B, N, _ = embeddings.shape
+            w_hi, w_lo = native.split_tf32(wcat)
+            cache = native.gemm_tf32x3(embeddings.detach().reshape(B * N, E), w_hi, w_lo).view(B, N, -1)
+        else:
+            cache = torch.nn.functional.linear(embeddings, wcat)
         if self.use_graph_context:
             graph_context = self.project_fixed_context(embeddings.mean(1))
         else:
