@@ -14,31 +14,35 @@
 // accumulates hi*hi + lo*hi + hi*lo in fp32 TMEM accumulators (the dropped lo*lo term is
 // ~2^-22 relative), i.e. fp32-class accuracy (~1e-6 relative) at tensor-core rate.
 //
-// Structure (one CTA per 128x128 output tile, 256 threads, 64 KB smem -> 3 CTAs/SM overlap each
+// Structure (one CTA per 128x128 output tile, 256 threads, 64 KB smem, 2-3 CTAs/SM overlap each
 // other's load / MMA / epilogue phases):
-//   for each 32-wide k-block:  all warps LDG A / W_hi / W_lo -> split A -> STS in the UMMA
-//   canonical K-major no-swizzle layout ((8 rows x 16 B) core matrices, LBO = 128 B, SBO = 1 KB)
-//   -> fence.proxy.async -> one elected thread issues 12 tcgen05.mma (4 k-steps x 3 products)
-//   -> tcgen05.commit -> mbarrier wait.  Epilogue: 4 warps tcgen05.ld 32x32b.x32 their TMEM
-//   lanes, apply the fused epilogue, 128-bit stores.
+//   per 32-wide k-block: the k-block's A / W_hi / W_lo float4s are prefetched into registers
+//   while the previous k-block's MMAs run; then split A -> STS into 128-byte-swizzled K-major
+//   tiles (row r at r*128 B, 16-byte chunk c stored at c ^ (r & 7); SBO = 1 KB) ->
+//   fence.proxy.async -> one elected thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x 3
+//   products hi*hi, lo*hi, hi*lo) -> tcgen05.commit -> mbarrier.
+//   Epilogue: all 8 warps tcgen05.ld 32x32b.x32 their TMEM lanes, transpose through swizzled
+//   shared memory, apply the fused epilogue and store full 128-byte row segments.
 #include "co_common.cuh"
 
 namespace co {
 
 constexpr int GM = 128, GN = 128, GK = 32;
 constexpr int TILE_BYTES = GM * GK * 4;  // 16 KB per operand tile
-constexpr uint32_t LBO = 128, SBO = 1024;
+constexpr uint32_t SBO = 1024;  // 8 rows x 128 B swizzle atom
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  // cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
-  // SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_NONE [61,64)
+  // cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30) (unused
+  // for swizzled K-major, canonical value 1), SBO>>4 [32,46), version=1 [46,48),
+  // layout_type=SWIZZLE_128B (2) [61,64)
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(LBO >> 4) << 16;
+  d |= (uint64_t)1 << 16;
   d |= (uint64_t)(SBO >> 4) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 
@@ -78,7 +82,7 @@ struct GemmArgs {
   int M, Nout, K, lda, ldc, ldr, relu, n_tiles;
 };
 
-__global__ void __launch_bounds__(256, 3) gemm_tf32x3_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(256, 2) gemm_tf32x3_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sAhi = smem;
   unsigned char* sAlo = smem + TILE_BYTES;
@@ -104,66 +108,77 @@ __global__ void __launch_bounds__(256, 3) gemm_tf32x3_kernel(const GemmArgs g) {
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_d = tmem_base_s;
 
-  // load mapping: a warp covers 8 rows x 4 chunks(16 B) -> 512 contiguous smem bytes, 8 x 64 B global segments
+  // load mapping: a warp covers 8 rows x 4 chunks(16 B): 8 x 64 B global segments, and -- with the
+  // 128B swizzle -- 8 distinct bank groups per quarter-warp on the shared-memory side
   const int r8 = lane & 7, c4 = lane >> 3;
-  uint32_t phase = 0;
   const int nkb = g.K / GK;
-  for (int kb = 0; kb < nkb; ++kb) {
+  float4 pa[4], ph[4], pl[4];
+  auto prefetch = [&](int kb) {
     const int k0 = kb * GK;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int q = warp + 8 * j;              // 32 (row-group, chunk-half) items per tile
-      const int rg = q >> 1, chunk = 4 * (q & 1) + c4;
-      const int row = 8 * rg + r8;
-      const uint32_t soff = rg * SBO + chunk * LBO + r8 * 16;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bh = a, bl = a;
-      if (m0 + row < g.M) a = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)(m0 + row) * g.lda + k0 + chunk * 4));
+      const int q = warp + 8 * j;  // 32 (row-group, chunk-half) items per tile
+      const int row = 8 * (q >> 1) + r8, chunk = 4 * (q & 1) + c4;
+      pa[j] = make_float4(0.f, 0.f, 0.f, 0.f); ph[j] = pa[j]; pl[j] = pa[j];
+      if (m0 + row < g.M) pa[j] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)(m0 + row) * g.lda + k0 + chunk * 4));
       if (n0 + row < g.Nout) {
-        bh = __ldg(reinterpret_cast<const float4*>(g.Whi + (size_t)(n0 + row) * g.K + k0 + chunk * 4));
-        bl = __ldg(reinterpret_cast<const float4*>(g.Wlo + (size_t)(n0 + row) * g.K + k0 + chunk * 4));
+        ph[j] = __ldg(reinterpret_cast<const float4*>(g.Whi + (size_t)(n0 + row) * g.K + k0 + chunk * 4));
+        pl[j] = __ldg(reinterpret_cast<const float4*>(g.Wlo + (size_t)(n0 + row) * g.K + k0 + chunk * 4));
       }
-      const float4 ah = split_hi(a);
-      const float4 al = make_float4(a.x - ah.x, a.y - ah.y, a.z - ah.z, a.w - ah.w);
+    }
+  };
+  auto wait_mma = [&](uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t bar = smem_u32(&mbar);
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+  };
+  prefetch(0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (kb > 0) wait_mma((kb - 1) & 1);  // MMAs of the previous k-block have consumed the smem stage
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = warp + 8 * j;
+      const int rg = q >> 1, chunk = 4 * (q & 1) + c4;
+      const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+      const float4 ah = split_hi(pa[j]);
+      const float4 al = make_float4(pa[j].x - ah.x, pa[j].y - ah.y, pa[j].z - ah.z, pa[j].w - ah.w);
       *reinterpret_cast<float4*>(sAhi + soff) = ah;
       *reinterpret_cast<float4*>(sAlo + soff) = al;
-      *reinterpret_cast<float4*>(sBhi + soff) = bh;
-      *reinterpret_cast<float4*>(sBlo + soff) = bl;
+      *reinterpret_cast<float4*>(sBhi + soff) = ph[j];
+      *reinterpret_cast<float4*>(sBlo + soff) = pl[j];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async-proxy (MMA) reads
     __syncthreads();
+    if (kb + 1 < nkb) prefetch(kb + 1);  // global loads fly while the tensor core works
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
       const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo), bhi = smem_u32(sBhi), blo = smem_u32(sBlo);
 #pragma unroll
-      for (int kk = 0; kk < GK / 8; ++kk) {     // UMMA_K = 8 tf32 = 2 core matrices along K
-        const uint32_t off = kk * 2 * LBO;
+      for (int kk = 0; kk < GK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 B: advance inside the swizzle atom
+        const uint32_t off = kk * 32;
         mma_tf32(tmem_d, make_desc(ahi + off), make_desc(bhi + off), (kb | kk) != 0);
         mma_tf32(tmem_d, make_desc(alo + off), make_desc(bhi + off), 1);
         mma_tf32(tmem_d, make_desc(ahi + off), make_desc(blo + off), 1);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
     }
-    // wait until the MMAs have consumed this stage (also: accumulator complete after the last one)
-    {
-      uint32_t done = 0;
-      const uint32_t bar = smem_u32(&mbar);
-      while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-      }
-      phase ^= 1;
-    }
   }
+  wait_mma((nkb - 1) & 1);  // accumulator complete; operand tiles free (reused as staging below)
   asm volatile("tcgen05.fence::after_thread_sync;");
 
-  // ---- epilogue: warps 0..3 own TMEM lanes 32w..32w+31 = output rows
-  if (warp < 4) {
-    const int row = m0 + 32 * warp + lane;
-    const bool row_ok = row < g.M;
+  // ---- epilogue: warp w reads TMEM lanes 32(w%4).. (rows) x 64 columns [(w/4)*64, +64)
+  {
+    const int wq = warp & 3, chalf = warp >> 2;
+    float* stage = reinterpret_cast<float*>(smem) + warp * 1024;  // 32 rows x 32 floats, chunk-swizzled
+    const int rr = lane >> 3, v = lane & 7;                       // store mapping: 4 rows x 8 chunks per instruction
 #pragma unroll 1
-    for (int cc = 0; cc < GN / 32; ++cc) {
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int cc = chalf * 2 + c2;
       uint32_t r[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * warp) << 16) + cc * 32;
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * wq) << 16) + cc * 32;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -174,35 +189,32 @@ __global__ void __launch_bounds__(256, 3) gemm_tf32x3_kernel(const GemmArgs g) {
             "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + cc * 32;
-      if (row_ok) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const int n = nb + 4 * v;
-          if (n < g.Nout) {
-            float o[4] = {__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
-                          __uint_as_float(r[4 * v + 3])};
-            if (g.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-              o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
-            }
-            if (g.residual) {
-              const float4 x = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n));
-              o[0] += x.x; o[1] += x.y; o[2] += x.z; o[3] += x.w;
-            }
-            if (g.relu) {
+      for (int u = 0; u < 8; ++u)  // thread = row `lane`: chunk u stored at u ^ (lane & 7)
+        *reinterpret_cast<uint4*>(stage + lane * 32 + ((u ^ (lane & 7)) << 2)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+      __syncwarp();
+      const int n = n0 + cc * 32 + 4 * v;
+      const bool n_ok = n < g.Nout;
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bs;
+      if (n_ok && g.bias) bs = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if (n_ok && g.scale) { sc4 = __ldg(reinterpret_cast<const float4*>(g.scale + n)); sh4 = __ldg(reinterpret_cast<const float4*>(g.shift + n)); }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-            }
-            if (g.scale) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(g.scale + n));
-              const float4 t = __ldg(reinterpret_cast<const float4*>(g.shift + n));
-              o[0] = fmaf(o[0], s.x, t.x); o[1] = fmaf(o[1], s.y, t.y); o[2] = fmaf(o[2], s.z, t.z); o[3] = fmaf(o[3], s.w, t.w);
-            }
-            *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int i = 0; i < 8; ++i) {
+        const int lrow = 4 * i + rr;
+        const int row = m0 + 32 * wq + lrow;
+        float4 o = *reinterpret_cast<const float4*>(stage + lrow * 32 + ((v ^ (lrow & 7)) << 2));
+        if (row < g.M && n_ok) {
+          o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
+          if (g.residual) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n));
+            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
           }
+          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (g.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
+          *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
         }
       }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
