@@ -82,6 +82,59 @@ struct GemmArgs {
   int M, Nout, K, lda, ldc, ldr, relu, n_tiles;
 };
 
+// all 8 warps: warp w reads TMEM lanes 32(w%4).. (rows) x 64 columns [(w/4)*64, +64), transposes
+// through chunk-swizzled shared memory (`smem`: 8 x 4 KB) and stores 4 rows x 128 B per instruction
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, unsigned char* smem, uint32_t tmem_d, int m0, int n0,
+                                              int warp, int lane) {
+  {
+    const int wq = warp & 3, chalf = warp >> 2;
+    float* stage = reinterpret_cast<float*>(smem) + warp * 1024;  // 32 rows x 32 floats, chunk-swizzled
+    const int rr = lane >> 3, v = lane & 7;                       // store mapping: 4 rows x 8 chunks per instruction
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int cc = chalf * 2 + c2;
+      uint32_t r[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * wq) << 16) + cc * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < 8; ++u)  // thread = row `lane`: chunk u stored at u ^ (lane & 7)
+        *reinterpret_cast<uint4*>(stage + lane * 32 + ((u ^ (lane & 7)) << 2)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+      __syncwarp();
+      const int n = n0 + cc * 32 + 4 * v;
+      const bool n_ok = n < g.Nout;
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bs;
+      if (n_ok && g.bias) bs = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if (n_ok && g.scale) { sc4 = __ldg(reinterpret_cast<const float4*>(g.scale + n)); sh4 = __ldg(reinterpret_cast<const float4*>(g.shift + n)); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int lrow = 4 * i + rr;
+        const int row = m0 + 32 * wq + lrow;
+        float4 o = *reinterpret_cast<const float4*>(stage + lrow * 32 + ((v ^ (lrow & 7)) << 2));
+        if (row < g.M && n_ok) {
+          o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
+          if (g.residual) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n));
+            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          }
+          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (g.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
+          *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 2) gemm_tf32x3_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sAhi = smem;
@@ -169,59 +222,120 @@ __global__ void __launch_bounds__(256, 2) gemm_tf32x3_kernel(const GemmArgs g) {
   wait_mma((nkb - 1) & 1);  // accumulator complete; operand tiles free (reused as staging below)
   asm volatile("tcgen05.fence::after_thread_sync;");
 
-  // ---- epilogue: warp w reads TMEM lanes 32(w%4).. (rows) x 64 columns [(w/4)*64, +64)
-  {
-    const int wq = warp & 3, chalf = warp >> 2;
-    float* stage = reinterpret_cast<float*>(smem) + warp * 1024;  // 32 rows x 32 floats, chunk-swizzled
-    const int rr = lane >> 3, v = lane & 7;                       // store mapping: 4 rows x 8 chunks per instruction
-#pragma unroll 1
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int cc = chalf * 2 + c2;
-      uint32_t r[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * wq) << 16) + cc * 32;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int u = 0; u < 8; ++u)  // thread = row `lane`: chunk u stored at u ^ (lane & 7)
-        *reinterpret_cast<uint4*>(stage + lane * 32 + ((u ^ (lane & 7)) << 2)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
-      __syncwarp();
-      const int n = n0 + cc * 32 + 4 * v;
-      const bool n_ok = n < g.Nout;
-      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bs;
-      if (n_ok && g.bias) bs = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-      if (n_ok && g.scale) { sc4 = __ldg(reinterpret_cast<const float4*>(g.scale + n)); sh4 = __ldg(reinterpret_cast<const float4*>(g.shift + n)); }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int lrow = 4 * i + rr;
-        const int row = m0 + 32 * wq + lrow;
-        float4 o = *reinterpret_cast<const float4*>(stage + lrow * 32 + ((v ^ (lrow & 7)) << 2));
-        if (row < g.M && n_ok) {
-          o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
-          if (g.residual) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n));
-            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-          }
-          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (g.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
-          *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
-        }
-      }
-      __syncwarp();
-    }
-  }
+  epilogue_tile(g, smem, tmem_d, m0, n0, warp, lane);
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(GN));
   }
+}
+
+
+// ---- W-stationary variant for K == 128 (all the K=128 projections of the path): a persistent CTA
+// keeps its 128-column W tile (hi + lo, 4 k-blocks, 128 KB) in shared memory and streams M tiles
+// through one 32 KB A stage, so per output tile only the 64 KB A tile crosses L2 -> SM.
+constexpr int KB128 = 4;
+__global__ void __launch_bounds__(256, 1) gemm_tf32x3_wstat_kernel(const GemmArgs g, int m_tiles, int groups) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sAhi = smem;                    // also the epilogue staging (8 x 4 KB)
+  unsigned char* sAlo = smem + TILE_BYTES;
+  unsigned char* sW = smem + 2 * TILE_BYTES;     // [kb][hi, lo] 16 KB each
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x % g.n_tiles, group = blockIdx.x / g.n_tiles;
+  const int n0 = n_tile * GN;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(GN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  const int r8 = lane & 7, c4 = lane >> 3;
+  // resident W tile
+  for (int kb = 0; kb < KB128; ++kb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = warp + 8 * j;
+      const int rg = q >> 1, chunk = 4 * (q & 1) + c4, row = 8 * rg + r8;
+      const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+      if (n0 + row < g.Nout) {
+        h = __ldg(reinterpret_cast<const float4*>(g.Whi + (size_t)(n0 + row) * g.K + kb * GK + chunk * 4));
+        l = __ldg(reinterpret_cast<const float4*>(g.Wlo + (size_t)(n0 + row) * g.K + kb * GK + chunk * 4));
+      }
+      *reinterpret_cast<float4*>(sW + (2 * kb) * TILE_BYTES + soff) = h;
+      *reinterpret_cast<float4*>(sW + (2 * kb + 1) * TILE_BYTES + soff) = l;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_d = tmem_base_s;
+
+  float4 pa[4];
+  auto prefetch = [&](int mt, int kb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = warp + 8 * j;
+      const int row = mt * GM + 8 * (q >> 1) + r8, chunk = 4 * (q & 1) + c4;
+      pa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mt < m_tiles && row < g.M) pa[j] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + kb * GK + chunk * 4));
+    }
+  };
+  uint32_t commits = 0;  // number of tcgen05.commit issued so far (mbarrier phase = commits & 1)
+  auto wait_mma = [&](uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t bar = smem_u32(&mbar);
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+  };
+  int mt = group;
+  prefetch(mt, 0);
+  for (; mt < m_tiles; mt += groups) {
+    for (int kb = 0; kb < KB128; ++kb) {
+      if (kb > 0) wait_mma((commits - 1) & 1);  // previous k-block's MMAs have consumed the A stage
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = warp + 8 * j;
+        const int rg = q >> 1, chunk = 4 * (q & 1) + c4;
+        const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+        const float4 ah = split_hi(pa[j]);
+        *reinterpret_cast<float4*>(sAhi + soff) = ah;
+        *reinterpret_cast<float4*>(sAlo + soff) = make_float4(pa[j].x - ah.x, pa[j].y - ah.y, pa[j].z - ah.z, pa[j].w - ah.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (kb + 1 < KB128) prefetch(mt, kb + 1); else prefetch(mt + groups, 0);
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t ahi = smem_u32(sAhi), alo = smem_u32(sAlo);
+        const uint32_t bhi = smem_u32(sW + (2 * kb) * TILE_BYTES), blo = smem_u32(sW + (2 * kb + 1) * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < GK / 8; ++kk) {
+          const uint32_t off = kk * 32;
+          mma_tf32(tmem_d, make_desc(ahi + off), make_desc(bhi + off), (kb | kk) != 0);
+          mma_tf32(tmem_d, make_desc(alo + off), make_desc(bhi + off), 1);
+          mma_tf32(tmem_d, make_desc(ahi + off), make_desc(blo + off), 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+      }
+      ++commits;
+    }
+    wait_mma((commits - 1) & 1);  // accumulator complete, A stage free (reused as staging)
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    epilogue_tile(g, smem, tmem_d, mt * GM, n0, warp, lane);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();  // staging reads and TMEM reads done before the next tile's stores / MMAs
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(GN));
 }
 
 }  // namespace co
@@ -253,8 +367,17 @@ extern "C" int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TILE_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tf32x3_wstat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * KB128) * TILE_BYTES);
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
     configured = true;
+  }
+  const int m_tiles = (M + GM - 1) / GM;
+  const int sms = device_info().sm_count;
+  if (K == GK * KB128 && g.n_tiles <= sms && m_tiles >= 4 * (sms / g.n_tiles)) {
+    const int groups = sms / g.n_tiles;  // CTAs of one group share an M tile (L2 reuse of A)
+    gemm_tf32x3_wstat_kernel<<<groups * g.n_tiles, 256, (2 + 2 * KB128) * TILE_BYTES, (cudaStream_t)stream>>>(g, m_tiles, groups);
+    return check_launch("co_gemm_tf32x3(wstat)");
   }
   gemm_tf32x3_kernel<<<(unsigned)tiles, 256, 4 * TILE_BYTES, (cudaStream_t)stream>>>(g);
   return check_launch("co_gemm_tf32x3");

@@ -20,7 +20,8 @@ def _ref(a, w, bias, residual, scale, shift, relu):
     return c
 
 
-@pytest.mark.parametrize("M,K,Nout", [(128, 128, 128), (1000, 128, 384), (777, 512, 128), (4096, 128, 640), (130, 128, 512)])
+@pytest.mark.parametrize("M,K,Nout", [(128, 128, 128), (1000, 128, 384), (777, 512, 128), (4096, 128, 640), (130, 128, 512),
+                                      (76877, 128, 640), (70001, 128, 128), (80000, 128, 384)])  # last 3: W-stationary path
 @pytest.mark.parametrize("epi", ["plain", "bias_relu", "residual_affine"])
 def test_gemm_tf32x3_matches_fp64(M, K, Nout, epi):
     from rl4co_b200 import native
