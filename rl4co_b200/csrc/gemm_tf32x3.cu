@@ -23,6 +23,8 @@
 //   products hi*hi, lo*hi, hi*lo) -> tcgen05.commit -> mbarrier.
 //   Epilogue: all 8 warps tcgen05.ld 32x32b.x32 their TMEM lanes, transpose through swizzled
 //   shared memory, apply the fused epilogue and store full 128-byte row segments.
+#include <stdlib.h>
+
 #include "co_common.cuh"
 
 namespace co {
@@ -84,15 +86,20 @@ struct GemmArgs {
 
 // all 8 warps: warp w reads TMEM lanes 32(w%4).. (rows) x 64 columns [(w/4)*64, +64), transposes
 // through chunk-swizzled shared memory (`smem`: 8 x 4 KB) and stores 4 rows x 128 B per instruction
+__device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, float* stage, uint32_t tmem_d, int m0, int n0, int wq,
+                                                int cc_begin, int cc_count, int lane);
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, unsigned char* smem, uint32_t tmem_d, int m0, int n0,
                                               int warp, int lane) {
+  epilogue_chunks(g, reinterpret_cast<float*>(smem) + warp * 1024, tmem_d, m0, n0, warp & 3, (warp >> 2) * 2, 2, lane);
+}
+// warp-level: rows 32*wq.. of the tile, column chunks [cc_begin, cc_begin + cc_count) of 32 columns each
+__device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, float* stage, uint32_t tmem_d, int m0, int n0, int wq,
+                                                int cc_begin, int cc_count, int lane) {
   {
-    const int wq = warp & 3, chalf = warp >> 2;
-    float* stage = reinterpret_cast<float*>(smem) + warp * 1024;  // 32 rows x 32 floats, chunk-swizzled
-    const int rr = lane >> 3, v = lane & 7;                       // store mapping: 4 rows x 8 chunks per instruction
+    const int rr = lane >> 3, v = lane & 7;  // store mapping: 4 rows x 8 chunks per instruction
 #pragma unroll 1
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int cc = chalf * 2 + c2;
+    for (int c2 = 0; c2 < cc_count; ++c2) {
+      const int cc = cc_begin + c2;
       uint32_t r[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(32 * wq) << 16) + cc * 32;
       asm volatile(
@@ -338,6 +345,171 @@ __global__ void __launch_bounds__(256, 1) gemm_tf32x3_wstat_kernel(const GemmArg
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(GN));
 }
 
+
+// ---- warp-specialised W-stationary pipeline for K == 128 (the fast path):
+//   warps 0-3  producers : LDG A (one full tile = 4 k-blocks prefetched in registers a tile ahead)
+//                          -> hi/lo split -> STS into a 2-stage ring of swizzled A tiles
+//   warps 4-7  epilogue  : TMEM -> registers -> swizzled staging -> fused epilogue -> 128 B row stores
+//   warp  8    MMA issuer: waits full[s], issues 12 tcgen05.mma per k-block, commits to empty[s];
+//                          accumulators double-buffered in TMEM (2 x 128 columns)
+// so loads, tensor-core work and stores of consecutive tiles overlap inside one persistent CTA.
+constexpr int PIPE_THREADS = 288;
+constexpr int A_STAGES = 2;
+constexpr int PIPE_SMEM = 2 * KB128 * TILE_BYTES + A_STAGES * 2 * TILE_BYTES + 4 * 4096;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) gemm_tf32x3_pipe_kernel(const GemmArgs g, int m_tiles, int groups) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sW = smem;                                   // [kb][hi, lo] 16 KB each (128 KB)
+  unsigned char* sA = smem + 2 * KB128 * TILE_BYTES;          // [stage][hi, lo]
+  float* sStage = reinterpret_cast<float*>(sA + A_STAGES * 2 * TILE_BYTES);  // 4 x 4 KB
+  __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 4];    // full[2], empty[2], tfull[2], tempty[2]
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tile = blockIdx.x % g.n_tiles, group = blockIdx.x / g.n_tiles;
+  const int n0 = n_tile * GN;
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL_B = [&](int s) { return bar0 + 8 * s; };
+  auto EMPTY_B = [&](int s) { return bar0 + 8 * (A_STAGES + s); };
+  auto TFULL_B = [&](int a) { return bar0 + 8 * (2 * A_STAGES + a); };
+  auto TEMPTY_B = [&](int a) { return bar0 + 8 * (2 * A_STAGES + 2 + a); };
+
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * GN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < A_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(FULL_B(s)), "r"(128));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY_B(s)), "r"(1));
+    }
+    for (int a = 0; a < 2; ++a) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(TFULL_B(a)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(TEMPTY_B(a)), "r"(128));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  // resident W tile: all 288 threads, item = (kb, row-group, chunk-half); a warp covers 8 rows x 4 chunks
+  {
+    const int r8 = lane & 7, c4 = lane >> 3;
+    for (int item = warp; item < KB128 * 32; item += PIPE_THREADS / 32) {
+      const int kb = item >> 5, q = item & 31;
+      const int rg = q >> 1, chunk = 4 * (q & 1) + c4, row = 8 * rg + r8;
+      const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+      if (n0 + row < g.Nout) {
+        h = __ldg(reinterpret_cast<const float4*>(g.Whi + (size_t)(n0 + row) * g.K + kb * GK + chunk * 4));
+        l = __ldg(reinterpret_cast<const float4*>(g.Wlo + (size_t)(n0 + row) * g.K + kb * GK + chunk * 4));
+      }
+      *reinterpret_cast<float4*>(sW + (2 * kb) * TILE_BYTES + soff) = h;
+      *reinterpret_cast<float4*>(sW + (2 * kb + 1) * TILE_BYTES + soff) = l;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int r8 = lane & 7, c4 = lane >> 3;
+    float4 R[KB128][8];
+    auto prefetch = [&](int mt, int kb) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = warp + 4 * j;  // 32 (row-group, chunk-half) items per k-block
+        const int row = mt * GM + 8 * (q >> 1) + r8, chunk = 4 * (q & 1) + c4;
+        R[kb][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mt < m_tiles && row < g.M)
+          R[kb][j] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + kb * GK + chunk * 4));
+      }
+    };
+#pragma unroll
+    for (int kb = 0; kb < KB128; ++kb) prefetch(group, kb);
+    uint32_t it = 0;
+    for (int mt = group; mt < m_tiles; mt += groups) {
+#pragma unroll
+      for (int kb = 0; kb < KB128; ++kb) {
+        const int s = it & 1;
+        mbar_wait(EMPTY_B(s), ((it >> 1) & 1) ^ 1);
+        unsigned char* ahi = sA + (2 * s) * TILE_BYTES;
+        unsigned char* alo = ahi + TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = warp + 4 * j;
+          const int rg = q >> 1, chunk = 4 * (q & 1) + c4;
+          const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+          const float4 a = R[kb][j], h = split_hi(a);
+          *reinterpret_cast<float4*>(ahi + soff) = h;
+          *reinterpret_cast<float4*>(alo + soff) = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(FULL_B(s));
+        prefetch(mt + groups, kb);  // same k-block of the next tile: a whole tile time to land
+        ++it;
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t it = 0, tc = 0;
+      for (int mt = group; mt < m_tiles; mt += groups, ++tc) {
+        const int acc = tc & 1;
+        mbar_wait(TEMPTY_B(acc), ((tc >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t d = tmem_d + acc * GN;
+        for (int kb = 0; kb < KB128; ++kb, ++it) {
+          const int s = it & 1;
+          mbar_wait(FULL_B(s), (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t ahi = smem_u32(sA + (2 * s) * TILE_BYTES), alo = ahi + TILE_BYTES;
+          const uint32_t bhi = smem_u32(sW + (2 * kb) * TILE_BYTES), blo = bhi + TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < GK / 8; ++kk) {
+            const uint32_t off = kk * 32;
+            mma_tf32(d, make_desc(ahi + off), make_desc(bhi + off), (kb | kk) != 0);
+            mma_tf32(d, make_desc(alo + off), make_desc(bhi + off), 1);
+            mma_tf32(d, make_desc(ahi + off), make_desc(blo + off), 1);
+          }
+          umma_commit(EMPTY_B(s));  // A stage reusable once these MMAs have read it
+        }
+        umma_commit(TFULL_B(acc));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 4..7
+    const int wq = warp & 3;
+    uint32_t tc = 0;
+    for (int mt = group; mt < m_tiles; mt += groups, ++tc) {
+      const int acc = tc & 1;
+      mbar_wait(TFULL_B(acc), (tc >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      epilogue_chunks(g, sStage + wq * 1024, tmem_d + acc * GN, mt * GM, n0, wq, 0, GN / 32, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      mbar_arrive(TEMPTY_B(acc));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * GN));
+}
+
 }  // namespace co
 
 using namespace co;
@@ -369,6 +541,8 @@ extern "C" int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TILE_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_tf32x3_wstat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 + 2 * KB128) * TILE_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tf32x3_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_gemm_tf32x3: smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -376,8 +550,13 @@ extern "C" int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo
   const int sms = device_info().sm_count;
   if (K == GK * KB128 && g.n_tiles <= sms && m_tiles >= 4 * (sms / g.n_tiles)) {
     const int groups = sms / g.n_tiles;  // CTAs of one group share an M tile (L2 reuse of A)
-    gemm_tf32x3_wstat_kernel<<<groups * g.n_tiles, 256, (2 + 2 * KB128) * TILE_BYTES, (cudaStream_t)stream>>>(g, m_tiles, groups);
-    return check_launch("co_gemm_tf32x3(wstat)");
+    static const int variant = getenv("CO_GEMM_VARIANT") ? atoi(getenv("CO_GEMM_VARIANT")) : 2;
+    if (variant == 1) {
+      gemm_tf32x3_wstat_kernel<<<groups * g.n_tiles, 256, (2 + 2 * KB128) * TILE_BYTES, (cudaStream_t)stream>>>(g, m_tiles, groups);
+      return check_launch("co_gemm_tf32x3(wstat)");
+    }
+    gemm_tf32x3_pipe_kernel<<<groups * g.n_tiles, PIPE_THREADS, PIPE_SMEM, (cudaStream_t)stream>>>(g, m_tiles, groups);
+    return check_launch("co_gemm_tf32x3(pipe)");
   }
   gemm_tf32x3_kernel<<<(unsigned)tiles, 256, 4 * TILE_BYTES, (cudaStream_t)stream>>>(g);
   return check_launch("co_gemm_tf32x3");
