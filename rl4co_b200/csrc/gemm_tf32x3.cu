@@ -427,16 +427,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) gemm_tf32x3_pipe_kernel(const
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
-    const int r8 = lane & 7, c4 = lane >> 3;
+    // lane -> (row % 4, 16-byte chunk 0..7): every LDG.128 instruction fetches 4 complete 128-byte
+    // rows of the k-block, and a quarter-warp writes one swizzled 128-byte row (conflict-free)
+    const int r4 = lane >> 3, c8 = lane & 7;
     float4 R[KB128][8];
     auto prefetch = [&](int mt, int kb) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int q = warp + 4 * j;  // 32 (row-group, chunk-half) items per k-block
-        const int row = mt * GM + 8 * (q >> 1) + r8, chunk = 4 * (q & 1) + c4;
+        const int row = mt * GM + 16 * j + 4 * warp + r4;
         R[kb][j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (mt < m_tiles && row < g.M)
-          R[kb][j] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + kb * GK + chunk * 4));
+          R[kb][j] = __ldg(reinterpret_cast<const float4*>(g.A + (size_t)row * g.lda + kb * GK + c8 * 4));
       }
     };
 #pragma unroll
@@ -451,9 +452,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) gemm_tf32x3_pipe_kernel(const
         unsigned char* alo = ahi + TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int q = warp + 4 * j;
-          const int rg = q >> 1, chunk = 4 * (q & 1) + c4;
-          const uint32_t soff = rg * SBO + r8 * 128 + ((chunk ^ r8) << 4);
+          const int lrow = 16 * j + 4 * warp + r4;  // row within the tile
+          const uint32_t soff = (lrow >> 3) * SBO + (lrow & 7) * 128 + ((c8 ^ (lrow & 7)) << 4);
           const float4 a = R[kb][j], h = split_hi(a);
           *reinterpret_cast<float4*>(ahi + soff) = h;
           *reinterpret_cast<float4*>(alo + soff) = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
