@@ -125,13 +125,75 @@ class AttentionModelEncoder(nn.Module):
     #: instances per forward chunk when no autograd graph is needed (bounds the FFN-hidden
     #: activation to chunk * N * 512 floats; exact because eval-mode norms are per element)
     inference_chunk = 8192
+    #: "tf32x3": Linear layers run on the hand-written tcgen05 3xTF32 GEMM (fp32-class accuracy)
+    #: with bias / ReLU / skip connection / eval-mode BatchNorm folded into its epilogue -- CUDA,
+    #: no-grad, eval only; "cublas": stock nn.Linear (strict fp32), always used under autograd.
+    gemm = "tf32x3"
 
     def forward(self, td, mask=None):
         init_h = self.init_embedding(td)
         B = init_h.shape[0]
-        if torch.is_grad_enabled() or self.training or B <= self.inference_chunk:
-            return self.net(init_h, mask), init_h
+        no_graph = not (torch.is_grad_enabled() or self.training)
+        fused = no_graph and self.gemm == "tf32x3" and init_h.is_cuda and isinstance(self.net, GraphAttentionNetwork)
+        run = self._net_fused if fused else (lambda x: self.net(x, mask))
+        if not no_graph or B <= self.inference_chunk:
+            return run(init_h), init_h
         out = torch.empty_like(init_h)
         for lo in range(0, B, self.inference_chunk):
-            out[lo:lo + self.inference_chunk] = self.net(init_h[lo:lo + self.inference_chunk], mask)
+            out[lo:lo + self.inference_chunk] = run(init_h[lo:lo + self.inference_chunk])
         return out, init_h
+
+    # ------------------------------------------------------------------ tensor-core inference path
+    def _split(self, w):
+        """(hi, lo) tf32 split of a weight, cached until the parameter is modified."""
+        from . import native
+
+        cache = self.__dict__.setdefault("_split_cache", {})
+        key = id(w)
+        ver = (w._version, w.data_ptr())
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, native.split_tf32(w))
+            cache[key] = hit
+        return hit[1]
+
+    @staticmethod
+    def _bn_affine(norm):
+        bn = norm.normalizer
+        if not isinstance(bn, nn.BatchNorm1d):
+            return None
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        return scale.contiguous(), (bn.bias - bn.running_mean * scale).contiguous()
+
+    def _net_fused(self, x):
+        """GraphAttentionNetwork.forward (nn/graph/attnnet.py:97-106) with every nn.Linear on
+        co_gemm_tf32x3; SkipConnection (nn/ops.py:9-15) = residual operand, eval BatchNorm
+        (nn/ops.py:30-46) = per-channel scale/shift of the same epilogue."""
+        from . import native
+
+        B, N, E = x.shape
+        h = x.reshape(B * N, E).contiguous()
+        for layer in self.net.layers:
+            mha, norm1, ffn, norm2 = layer[0].module, layer[1], layer[2].module, layer[3]
+            qkv = native.gemm_tf32x3(h, *self._split(mha.Wqkv.weight), bias=mha.Wqkv.bias)
+            q, k, v = qkv.view(B, N, 3, mha.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+            att = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, E)
+            aff = self._bn_affine(norm1)
+            if aff is not None:
+                h = native.gemm_tf32x3(att, *self._split(mha.out_proj.weight), bias=mha.out_proj.bias, residual=h,
+                                       scale=aff[0], shift=aff[1])
+            else:
+                h = native.gemm_tf32x3(att, *self._split(mha.out_proj.weight), bias=mha.out_proj.bias, residual=h)
+                h = norm1(h.view(B, N, E)).reshape(B * N, E).contiguous()
+            lins = ffn.lins
+            f = h
+            for lin in lins[:-1]:
+                f = native.gemm_tf32x3(f, *self._split(lin.weight), bias=lin.bias, relu=True)
+            aff = self._bn_affine(norm2)
+            if aff is not None:
+                h = native.gemm_tf32x3(f, *self._split(lins[-1].weight), bias=lins[-1].bias, residual=h,
+                                       scale=aff[0], shift=aff[1])
+            else:
+                h = native.gemm_tf32x3(f, *self._split(lins[-1].weight), bias=lins[-1].bias, residual=h)
+                h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()
+        return h.view(B, N, E)

@@ -344,6 +344,35 @@ def test_full_policy_vs_oracle_seeded(dev, env_name, n, batch, mode):
     _check_against_prefix_oracle(W, env_name, inst, h_gpu, out, mode, noise=noise)
 
 
+@pytest.mark.parametrize("env_name,norm", [("tsp", "batch"), ("cvrp", "instance")])
+def test_encoder_tensor_core_path_matches_fp32(dev, env_name, norm):
+    """Encoder with its Linear layers on co_gemm_tf32x3 (bias/ReLU/skip/BatchNorm in the GEMM
+    epilogue) vs the stock-PyTorch fp32 modules and vs the CPU oracle."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(3)
+    env = get_env(env_name, generator_params=dict(num_loc=50))
+    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=3, normalization=norm).eval()
+    for m in pol.modules():  # non-trivial running statistics
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    pol = pol.to(dev)
+    td_host = env.generator(300)
+    with torch.inference_mode():
+        td = env.reset(td_host.to(dev))
+        pol.encoder.gemm = "tf32x3"
+        h_tc, _ = pol.encoder(td)
+        pol.encoder.gemm = "cublas"
+        h_fp32, _ = pol.encoder(td)
+        st0 = O.env_reset(env_name, {k: td_host[k] for k in td_host.keys()})
+        h_ref, _ = O.encoder_forward(W, env_name, st0, num_layers=3, normalization=norm)
+    torch.testing.assert_close(h_tc, h_fp32, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(h_tc.cpu(), h_ref, rtol=1e-4, atol=1e-4)
+
+
 def test_sampling_philox_is_valid_and_seeded(dev):
     from rl4co_b200.envs import get_env
     from rl4co_b200.policy import FusedAttentionModelPolicy
