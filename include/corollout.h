@@ -208,6 +208,11 @@ int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo, float* C,
                    const float* shift, int M, int Nout, int K, int lda, int ldc, int ldr,
                    int relu, void* stream);
 
+/* Encoder self-attention core: F.scaled_dot_product_attention of MultiHeadAttention
+ * (rl4co/models/nn/attention.py:110-134) on the packed projection qkv [B*N, 3E] ("three h d"),
+ * 8 heads x 16, no mask, fp32 -> out [B*N, E] ("h d"); N <= 128. */
+int co_encoder_mha(const float* qkv, float* out, int B, int N, void* stream);
+
 /* REINFORCE baseline statistics (rl4co/models/rl/reinforce/baselines.py:75-81):
  * out[0] += sum(reward), out[1] += count, in float64 so the cross-rank sum is
  * order-independent enough to reproduce the single-process mean. */

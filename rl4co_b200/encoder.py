@@ -176,8 +176,11 @@ class AttentionModelEncoder(nn.Module):
         for layer in self.net.layers:
             mha, norm1, ffn, norm2 = layer[0].module, layer[1], layer[2].module, layer[3]
             qkv = native.gemm_tf32x3(h, *self._split(mha.Wqkv.weight), bias=mha.Wqkv.bias)
-            q, k, v = qkv.view(B, N, 3, mha.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
-            att = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, E)
+            if N <= 128 and mha.num_heads == native.NUM_HEADS and E == native.EMBED_DIM:
+                att = native.encoder_mha(qkv, B, N)
+            else:
+                q, k, v = qkv.view(B, N, 3, mha.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+                att = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, E)
             aff = self._bn_affine(norm1)
             if aff is not None:
                 h = native.gemm_tf32x3(att, *self._split(mha.out_proj.weight), bias=mha.out_proj.bias, residual=h,

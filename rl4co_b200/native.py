@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "gemm_tf32x3.cu"]
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "gemm_tf32x3.cu", "encoder_mha.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh"]
 
 CO_OK = 0
@@ -33,7 +33,7 @@ EMBED_DIM, NUM_HEADS = 128, 8
 EXPORTS = [
     "co_version", "co_last_error_string", "co_device_sm_count", "co_tsp_step", "co_cvrp_action_mask",
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
-    "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3",
+    "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
 ]
 
 
@@ -126,6 +126,7 @@ def lib() -> ctypes.CDLL:
     L.co_cache_width.argtypes = [c_int]
     L.co_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]
     L.co_gemm_tf32x3.argtypes = [c_void_p] * 8 + [c_int] * 7 + [c_void_p]
+    L.co_encoder_mha.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
     _lib = L
     return L
 
@@ -281,6 +282,13 @@ def gemm_tf32x3(a, w_hi, w_lo, out=None, bias=None, residual=None, scale=None, s
                                 _ptr(scale, F32, "scale"), _ptr(shift, F32, "shift"), M, Nout, K, a.stride(0),
                                 out.stride(0), residual.stride(0) if residual is not None else 0, int(relu), _stream()),
            "co_gemm_tf32x3")
+    return out
+
+
+def encoder_mha(qkv, B, N):
+    """Self-attention core on the packed [B*N, 384] projection -> [B*N, 128]."""
+    out = torch.empty(B * N, EMBED_DIM, dtype=F32, device=qkv.device)
+    _check(lib().co_encoder_mha(_ptr(qkv, F32, "qkv"), _ptr(out, F32, "out"), B, N, _stream()), "co_encoder_mha")
     return out
 
 

@@ -373,6 +373,18 @@ def test_encoder_tensor_core_path_matches_fp32(dev, env_name, norm):
     torch.testing.assert_close(h_tc.cpu(), h_ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("B,N", [(3, 5), (7, 20), (64, 50), (9, 64), (33, 100), (5, 128), (2, 33)])
+def test_encoder_mha_kernel_vs_sdpa(dev, B, N):
+    from rl4co_b200 import native
+
+    torch.manual_seed(B * N)
+    qkv = torch.randn(B * N, 384, device=dev) * 1.5
+    out = native.encoder_mha(qkv, B, N)
+    q, k, v = qkv.view(B, N, 3, 8, 16).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(B * N, 128)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
 def test_sampling_philox_is_valid_and_seeded(dev):
     from rl4co_b200.envs import get_env
     from rl4co_b200.policy import FusedAttentionModelPolicy
