@@ -131,7 +131,13 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+#: number of libcorollout kernel launches issued through this module (bench.py's gpu_launches)
+LAUNCH_COUNT = 0
+
+
 def _check(rc: int, what: str) -> None:
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
     if rc != CO_OK:
         msg = lib().co_last_error_string().decode("utf-8", "replace")
         raise NativeLibraryError(f"{what} failed with code {rc}: {msg}")
