@@ -60,8 +60,10 @@ class FusedAttentionModelPolicy(nn.Module):
     def forward(self, td: TensorDict, env=None, phase: str = "train", calc_reward: bool = True,
                 return_actions: bool = True, return_entropy: bool = False, return_hidden: bool = False,
                 return_init_embeds: bool = False, return_sum_log_likelihood: bool = True, actions=None,
-                max_steps=1_000_000, **decoding_kwargs) -> dict:
-        hidden, init_embeds = self.encoder(td)
+                max_steps=1_000_000, encoder_output=None, **decoding_kwargs) -> dict:
+        # `encoder_output=(hidden, init_embeds)` reuses an encoder pass (e.g. the differentiable one of a
+        # training step) instead of running the encoder again
+        hidden, init_embeds = self.encoder(td) if encoder_output is None else encoder_output
         if isinstance(env, str) or env is None:
             env = get_env(self.env_name if env is None else env)
 

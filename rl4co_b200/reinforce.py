@@ -1,0 +1,252 @@
+"""REINFORCE / POMO glue around the fused rollout.
+
+  REINFORCE.shared_step / calculate_loss   rl4co/models/rl/reinforce/reinforce.py:59-111
+  baselines (no / shared / mean / exponential / rollout)   rl4co/models/rl/reinforce/baselines.py:48-248
+  POMO.shared_step (dihedral-8 aug x multistart, max over starts / augs)   rl4co/models/zoo/pomo/model.py:88-143
+  Evaluate decoding (teacher forcing)      rl4co/utils/decoding.py:448-461, constructive/base.py:202-203
+
+Training needs d(log-likelihood)/d(theta).  The fused rollout kernel is forward-only, so a
+training step is:  (1) sample actions with the persistent kernel under no_grad;  (2) recompute the
+log-likelihood of exactly those actions with `evaluate_log_likelihood` -- a *vectorised*
+teacher-forced pass in differentiable PyTorch ops (all T decode steps of the whole batch in one
+masked attention call instead of the reference's T-iteration Python loop);  (3) REINFORCE loss.
+"""
+
+from __future__ import annotations
+
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+from .distributed import global_mean_baseline
+from .ops import StateAugmentation, batchify, gather_by_index, unbatchify
+from .tensordict import TensorDict
+
+E = native.EMBED_DIM
+
+
+# ------------------------------------------------------------------------ teacher-forced replay
+def replay_states(env_name: str, td: TensorDict, actions: torch.Tensor):
+    """Vectorised replay of the MDP along given actions [B,T]: returns (mask [B,T,N] bool,
+    cur [B,T] node before step t, first [B,T] (tsp), used [B,T] capacity before step t (cvrp)).
+    Restates tsp/env.py:60-86 and cvrp/env.py:66-136 without a time loop."""
+    B, T = actions.shape
+    N = td["locs"].shape[-2]
+    dev = actions.device
+    onehot = F.one_hot(actions, N)                                  # [B,T,N]
+    visited_before = (onehot.cumsum(1) - onehot) > 0               # visited strictly before step t
+    prev = torch.cat([torch.zeros(B, 1, dtype=actions.dtype, device=dev), actions[:, :-1]], 1)
+    if env_name == "tsp":
+        mask = ~visited_before
+        first = actions[:, :1].expand(B, T)
+        return mask, prev, first, None
+    demand = td["demand"]                                           # [B,N-1]
+    cap = td["vehicle_capacity"].reshape(B, 1)
+    dem_n = torch.cat([torch.zeros(B, 1, device=dev), demand], 1)   # node-indexed, depot 0
+    d_t = dem_n.gather(1, actions)                                  # demand served at step t
+    c = d_t.cumsum(1)                                               # non-decreasing
+    c_prev = torch.cat([torch.zeros(B, 1, device=dev), c[:, :-1]], 1)
+    at_depot = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=dev), actions[:, :-1] == 0], 1)
+    base = torch.where(at_depot, c_prev, torch.zeros_like(c_prev)).cummax(1)[0]
+    used = c_prev - base                                            # used capacity before step t
+    exceeds = (dem_n[:, None, 1:] + used[..., None]) > (cap[:, None] + 1e-5)
+    mask_loc = visited_before[..., 1:] | exceeds
+    mask_depot = (prev == 0)[..., None] & ((~mask_loc).sum(-1, keepdim=True) > 0)
+    return ~torch.cat([mask_depot, mask_loc], -1), prev, None, used
+
+
+def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, hidden=None,
+                            return_sum: bool = True) -> torch.Tensor:
+    """log pi(actions | instance) with autograd, equal (<= fp32 round-off) to what the rollout
+    kernel reported for the same actions.  `td` is the reset state (multistart: the [B] state,
+    actions [S*B, T] in the reference's start-major order)."""
+    env_name = env.name
+    dec = policy.decoder
+    if hidden is None:
+        hidden, _ = policy.encoder(td)
+    B, N, _ = hidden.shape
+    S = actions.shape[0] // B
+    T = actions.shape[1]
+    cached = dec._precompute_cache(hidden)
+    K, V = cached.glimpse_key, cached.glimpse_val
+    L = cached.logit_key
+    g = cached.graph_context if isinstance(cached.graph_context, torch.Tensor) else None
+    # trajectories of one instance become S*T queries against that instance's K / V / L (no copies)
+    acts = actions.view(S, B, T).permute(1, 0, 2).reshape(B * S, T) if S > 1 else actions   # instance-major
+    tdx = td
+    if S > 1:
+        tdx = TensorDict({k: td[k].repeat_interleave(S, 0) for k in ("locs", "demand", "vehicle_capacity") if k in td.keys()},
+                         batch_size=[B * S])
+    mask, prev, first, used = replay_states(env_name, tdx, acts)
+    Q = S * T
+    mask = mask.view(B, Q, N)
+    prev_q = prev.reshape(B, Q)
+    wc = dec.context_embedding.project_context.weight
+    forced_first = S > 1  # multistart: step 0 is the forced start node with log-prob 0
+    if env_name == "tsp":
+        ctx = torch.cat([gather_by_index(hidden, first.reshape(B, Q)), gather_by_index(hidden, prev_q)], -1)  # [B,Q,2E]
+        q = F.linear(ctx, wc)
+        if not forced_first:
+            q0 = F.linear(dec.context_embedding.W_placeholder, wc)
+            q = torch.cat([q0.expand(B, 1, E), q[:, 1:]], 1)
+    else:
+        cap = tdx["vehicle_capacity"].reshape(B * S, 1)
+        rem = (cap - used).reshape(B, Q, 1)
+        q = F.linear(torch.cat([gather_by_index(hidden, prev_q), rem], -1), wc)                                  # [B,Q,E]
+    if g is not None:
+        q = q + g[:, None, :]
+    H = native.NUM_HEADS
+
+    def heads(x):
+        return x.view(x.shape[0], x.shape[1], H, -1).transpose(1, 2)
+
+    o = F.scaled_dot_product_attention(heads(q), heads(K), heads(V), attn_mask=mask[:, None])
+    o = o.transpose(1, 2).reshape(B, Q, E)
+    glimpse = dec.pointer.project_out(o)
+    logits = torch.bmm(glimpse, L.transpose(1, 2)) / math.sqrt(E)
+    clip = policy.tanh_clipping
+    if clip > 0:
+        logits = torch.tanh(logits) * clip
+    logits = logits.masked_fill(~mask, float("-inf")) / policy.temperature
+    logp = F.log_softmax(logits, -1).gather(-1, acts.reshape(B, Q)[..., None]).squeeze(-1).view(B * S, T)
+    if forced_first:
+        logp = torch.cat([torch.zeros_like(logp[:, :1]), logp[:, 1:]], 1)
+    if S > 1:
+        logp = logp.view(B, S, T).permute(1, 0, 2).reshape(S * B, T)
+    return logp.sum(1) if return_sum else logp
+
+
+# ------------------------------------------------------------------------ baselines
+class NoBaseline:
+    """baselines.py:48-52"""
+
+    def eval(self, td, reward, env=None):
+        return 0, 0
+
+    def setup(self, *a, **k):
+        pass
+
+    def epoch_callback(self, *a, **k):
+        pass
+
+
+class SharedBaseline(NoBaseline):
+    """baselines.py:55-61: mean over the starts of each instance (POMO)."""
+
+    def eval(self, td, reward, env=None, on_dim=1):
+        return reward.mean(dim=on_dim, keepdims=True), 0
+
+
+class MeanBaseline(NoBaseline):
+    """baselines.py:75-81 with the mean taken over the GLOBAL batch: {sum, count} in f64 through
+    co_reward_stats + one NCCL all-reduce (the reference's DDP uses per-rank means)."""
+
+    def eval(self, td, reward, env=None):
+        return global_mean_baseline(reward.detach()), 0
+
+
+class ExponentialBaseline(NoBaseline):
+    """baselines.py:64-84"""
+
+    def __init__(self, beta=0.8):
+        self.beta, self.v = beta, None
+
+    def eval(self, td, reward, env=None):
+        m = global_mean_baseline(reward.detach())
+        self.v = m if self.v is None else self.beta * self.v + (1.0 - self.beta) * m
+        return self.v.detach(), 0
+
+
+class RolloutBaseline(NoBaseline):
+    """baselines.py:160-248 (greedy rollout of a frozen copy; the t-test epoch update is left to
+    the caller: `update(policy)` swaps the frozen copy)."""
+
+    def __init__(self):
+        self.policy = None
+
+    def setup(self, policy, *a, **k):
+        self.update(policy)
+
+    def update(self, policy):
+        self.policy = copy.deepcopy(policy).eval()
+        for p in self.policy.parameters():
+            p.requires_grad_(False)
+
+    def eval(self, td, reward, env=None):
+        with torch.inference_mode():
+            out = self.policy(td, env, phase="test", decode_type="greedy")
+        return out["reward"].clone(), 0
+
+
+def get_reinforce_baseline(name, **kw):
+    reg = {"no": NoBaseline, "shared": SharedBaseline, "mean": MeanBaseline, "exponential": ExponentialBaseline,
+           "rollout": RolloutBaseline}
+    if name not in reg:
+        raise ValueError(f"Unknown baseline {name}. Available baselines: {list(reg)}")
+    return reg[name](**kw)
+
+
+# ------------------------------------------------------------------------ REINFORCE / POMO steps
+def calculate_loss(reward, log_likelihood, bl_val, bl_loss=0):
+    """reinforce.py:96-111"""
+    advantage = reward - bl_val
+    reinforce_loss = -(advantage * log_likelihood).mean()
+    return reinforce_loss + bl_loss, reinforce_loss
+
+
+def reinforce_step(policy, env, td, baseline, optimizer=None, decode_type="sampling", seed=None, max_grad_norm=1.0):
+    """One REINFORCE training step (reinforce.py:59-111): fused sampling rollout (no grad) ->
+    differentiable log-likelihood of the sampled actions -> loss -> backward -> optimizer."""
+    policy.train()
+    enc = policy.encoder(td)  # ONE differentiable encoder pass (train-mode norms) shared by both stages
+    with torch.no_grad():
+        out = policy(td, env, phase="train", decode_type=decode_type, encoder_output=(enc[0].detach(), enc[1]),
+                     **({"seed": seed} if seed is not None else {}))
+    ll = evaluate_log_likelihood(policy, td, env, out["actions"], hidden=enc[0])
+    bl_val, bl_loss = baseline.eval(td, out["reward"], env)
+    loss, rl = calculate_loss(out["reward"], ll, bl_val, bl_loss)
+    if optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        if max_grad_norm:
+            torch.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)
+        optimizer.step()
+    return {"loss": loss.detach(), "reinforce_loss": rl.detach(), "reward": out["reward"], "log_likelihood": ll.detach(),
+            "bl_val": bl_val, "actions": out["actions"]}
+
+
+def pomo_step(policy, env, td, num_augment=8, num_starts=None, phase="test", optimizer=None):
+    """POMO.shared_step (pomo/model.py:88-143): optional dihedral-8 augmentation (val/test),
+    multistart rollout, shared baseline over starts; returns max rewards over starts / augs."""
+    B = td.batch_size[0]
+    n_aug = num_augment if phase != "train" else 0
+    n_start = env.get_num_starts(td) if num_starts is None else num_starts
+    if n_aug > 1:
+        td = StateAugmentation(num_augment=n_aug)(td)
+    if phase == "train":
+        policy.train()
+        enc = policy.encoder(td)
+        with torch.no_grad():
+            out = policy(td, env, phase="train", decode_type="multistart_sampling", num_starts=n_start,
+                         encoder_output=(enc[0].detach(), enc[1]))
+        ll = evaluate_log_likelihood(policy, td, env, out["actions"], hidden=enc[0])
+        reward = unbatchify(out["reward"], n_start)                       # [B, S]
+        bl_val, _ = SharedBaseline().eval(td, reward)
+        loss, _ = calculate_loss(reward, unbatchify(ll, n_start), bl_val)
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            optimizer.step()
+        return {"loss": loss.detach(), "reward": reward, "max_reward": reward.max(-1)[0]}
+    with torch.inference_mode():
+        out = policy(td, env, phase=phase, decode_type="multistart_greedy", num_starts=n_start)
+    shape = (n_aug, n_start) if n_aug > 1 else (n_start,)
+    reward = unbatchify(out["reward"], shape)                               # [B, aug, start] | [B, start]
+    max_reward = reward.max(-1)[0]
+    res = {"reward": reward, "max_reward": max_reward, "actions": out["actions"]}
+    if n_aug > 1:
+        res["max_aug_reward"] = max_reward.max(1)[0]
+    return res
