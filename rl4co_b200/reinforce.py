@@ -46,12 +46,14 @@ def replay_states(env_name: str, td: TensorDict, actions: torch.Tensor):
     demand = td["demand"]                                           # [B,N-1]
     cap = td["vehicle_capacity"].reshape(B, 1)
     dem_n = torch.cat([torch.zeros(B, 1, device=dev), demand], 1)   # node-indexed, depot 0
-    d_t = dem_n.gather(1, actions)                                  # demand served at step t
+    # prefix sums in float64: the difference of two fp32 prefix sums of magnitude ~10 would be off by
+    # more than the 1e-5 capacity slack on exact fits (the env accumulates the *current route* only)
+    d_t = dem_n.double().gather(1, actions)                         # demand served at step t
     c = d_t.cumsum(1)                                               # non-decreasing
-    c_prev = torch.cat([torch.zeros(B, 1, device=dev), c[:, :-1]], 1)
+    c_prev = torch.cat([torch.zeros(B, 1, dtype=torch.float64, device=dev), c[:, :-1]], 1)
     at_depot = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=dev), actions[:, :-1] == 0], 1)
     base = torch.where(at_depot, c_prev, torch.zeros_like(c_prev)).cummax(1)[0]
-    used = c_prev - base                                            # used capacity before step t
+    used = (c_prev - base).float()                                  # used capacity before step t
     exceeds = (dem_n[:, None, 1:] + used[..., None]) > (cap[:, None] + 1e-5)
     mask_loc = visited_before[..., 1:] | exceeds
     mask_depot = (prev == 0)[..., None] & ((~mask_loc).sum(-1, keepdim=True) > 0)

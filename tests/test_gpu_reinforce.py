@@ -35,6 +35,19 @@ def test_differentiable_loglik_matches_kernel(env_name, n, decode_type):
     assert lp.requires_grad
 
 
+def test_differentiable_loglik_is_finite_at_cvrp100():
+    """exact capacity fits (integer demands / 50) must replay as feasible: regression for the
+    fp32 prefix-sum replay that produced -inf log-probs."""
+    from rl4co_b200.reinforce import evaluate_log_likelihood
+
+    env, pol, td = _setup("cvrp", 100, 2048)
+    with torch.no_grad():
+        out = pol(td, env, decode_type="sampling", seed=5)
+        ll = evaluate_log_likelihood(pol, td, env, out["actions"])
+    assert torch.isfinite(ll).all()
+    torch.testing.assert_close(ll, out["log_likelihood"], rtol=2e-4, atol=2e-3)
+
+
 @pytest.mark.parametrize("env_name", ["tsp", "cvrp"])
 def test_replay_states_match_oracle_masks(env_name):
     from rl4co_b200.reinforce import replay_states
