@@ -62,6 +62,7 @@ struct Smem {
   float dem[32 * SPL];
   float2 loc[32 * SPL];
   unsigned char order[32 * SPL];    // cvrp: customers sorted by demand (ascending)
+  unsigned char vis_s[32 * SPL];    // cvrp: visited flags (every thread writes the same value itself)
   float ll_acc;
 };
 
@@ -181,20 +182,43 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 #pragma unroll
     for (int k = 0; k < SPL; ++k) dmk[k] = sm.dem[lane + 32 * k];
     const float dL = sm.dem[nL];
+    // scores split by linearity: q.K = ptab[cur].K + qfix.K + rem * (wcap.K); the last two are
+    // per-episode / per-instance constants held in registers (FK, WK)
+    auto head_dot = [&](const float* vec, float (&out)[SPL]) {
+      const float4* vp = reinterpret_cast<const float4*>(vec + h * D);
+      float2 a2[SPL];
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) a2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 x = vp[c];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+          a2[k] = ffma2(make_float2(x.x, x.y), Kr[k][2 * c], a2[k]);
+          a2[k] = ffma2(make_float2(x.z, x.w), Kr[k][2 * c + 1], a2[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) out[k] = a2[k].x + a2[k].y;
+    };
+    float WK[SPL], FK[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) { WK[k] = 0.f; FK[k] = 0.f; }
+    if (ENV == CO_ENV_CVRP) head_dot(sm.wcap, WK);
 
     for (int s = 0; s < S; ++s) {
       const int traj = s * B_inst + b;  // start-major, rl4co/utils/ops.py:10-29
       int64_t* act_row = A.actions_out + (size_t)traj * T_max;
       float* lp_row = A.logp_out + (size_t)traj * T_max;
       // ---------------- reset (tsp/env.py:88-113, cvrp/env.py:98-124)
-      uint32_t vis[SPL];
+      // visited flags this thread needs: bit k = its glimpse slot lane+32k, bit 8 = its logits node nL
+      // (padding slots start as visited)
+      uint32_t mybits = (nL >= N) ? 0x100u : 0u;
 #pragma unroll
-      for (int k = 0; k < SPL; ++k) {
-        const int lo = 32 * k;
-        vis[k] = (N >= lo + 32) ? 0u : (N <= lo ? 0xffffffffu : (0xffffffffu << (N - lo)));
-      }
+      for (int k = 0; k < SPL; ++k) mybits |= (lane + 32 * k >= N) ? (1u << k) : 0u;
+      if (ENV == CO_ENV_CVRP && tid < NS) sm.vis_s[tid] = 0;  // ordered before first use by the barrier below
       int cur = (ENV == CO_ENV_TSP) ? NS : 0;  // NS -> zero row: step-0 placeholder context
-      int prev = 0, first = 0, t = 0, dstep = 0, optr = 0;
+      int prev = 0, first = 0, t = 0, dstep = 0, optr = 0, nvis = 0;
       float used = 0.f, dist = 0.f;
       bool anyfeas = false, done = false;
       __syncthreads();  // previous trajectory finished with qfix / ll_acc
@@ -205,18 +229,11 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       if (tid == 0) sm.ll_acc = 0.f;
 
-      auto vis_bit = [&](int n) -> bool {  // select chain: no dynamic register indexing
-        uint32_t w = vis[0];
-#pragma unroll
-        for (int k = 1; k < SPL; ++k)
-          if ((n >> 5) == k) w = vis[k];
-        return (w >> (n & 31)) & 1u;
-      };
       // one environment transition, replicated in every thread
       auto env_step = [&](int a) {
 #pragma unroll
-        for (int k = 0; k < SPL; ++k)
-          if ((a >> 5) == k) vis[k] |= 1u << (a & 31);
+        for (int k = 0; k < SPL; ++k) mybits |= (a == lane + 32 * k) ? (1u << k) : 0u;
+        mybits |= (a == nL) ? 0x100u : 0u;
         if (h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
           const float2 pa = sm.loc[a], pp = sm.loc[prev];
           const float dx = pa.x - pp.x, dy = pa.y - pp.y;
@@ -226,17 +243,17 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           if (t == 0) first = a;
         } else {
           used = (used + sm.dem[a == 0 ? 1 : a]) * (a != 0 ? 1.0f : 0.0f);  // cvrp/env.py:70-76
+          // every thread records the visit itself, so its own later reads see it without a barrier
+          nvis += sm.vis_s[a] ? 0 : 1;
+          sm.vis_s[a] = 1;
           // depot rule (cvrp/env.py:134): any unvisited customer that still fits <=> the
           // unvisited customer of least demand fits (fp32 add is monotone in the demand)
           const int ncust = N - 1;
-          while (optr < ncust && vis_bit(sm.order[optr])) ++optr;
+          while (optr < ncust && sm.vis_s[sm.order[optr]]) ++optr;
           anyfeas = (optr < ncust) && !((sm.dem[sm.order[optr < ncust ? optr : 0]] + used) > thr);
         }
         prev = a; cur = a; ++t;
-        bool all = true;
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) all = all && (vis[k] == 0xffffffffu);
-        done = all;
+        done = (ENV == CO_ENV_TSP) ? (t >= N) : (nvis >= N);  // cvrp: all nodes incl. the depot visited
       };
 
       if (forced_start) {  // multistart pre_decoder_hook, decoding.py:309-326 + ops.py:128-149
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         anyfeas = !((sm.dem[sm.order[0]] + used) > thr);
       }
       __syncthreads();
+      head_dot(sm.qfix, FK);
 
       while (!done && t < T_max) {
         // early, latency-tolerant loads for this step
@@ -263,25 +281,17 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         // ---------------- glimpse: warp h = head h, fully warp-local
         {
           const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur * E + h * D);
-          const float4* qf = reinterpret_cast<const float4*>(sm.qfix + h * D);
-          const float4* wc = reinterpret_cast<const float4*>(sm.wcap + h * D);
           const float rem = cap - used;  // context.py:147-149
           float2 sc2[SPL];
 #pragma unroll
           for (int k = 0; k < SPL; ++k) sc2[k] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float4 p = pr[c], f = qf[c];
-            float2 qa = make_float2(p.x + f.x, p.y + f.y), qb = make_float2(p.z + f.z, p.w + f.w);
-            if (ENV == CO_ENV_CVRP) {
-              const float4 w = wc[c];
-              qa = ffma2(make_float2(w.x, w.y), make_float2(rem, rem), qa);
-              qb = ffma2(make_float2(w.z, w.w), make_float2(rem, rem), qb);
-            }
+            const float4 p = pr[c];
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
-              sc2[k] = ffma2(qa, Kr[k][2 * c], sc2[k]);
-              sc2[k] = ffma2(qb, Kr[k][2 * c + 1], sc2[k]);
+              sc2[k] = ffma2(make_float2(p.x, p.y), Kr[k][2 * c], sc2[k]);
+              sc2[k] = ffma2(make_float2(p.z, p.w), Kr[k][2 * c + 1], sc2[k]);
             }
           }
           // scores in log2 units: s * (1/sqrt(head_dim)) * log2(e)
@@ -289,8 +299,10 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           bool fz[SPL];
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
-            fz[k] = feasible<ENV>(lane + 32 * k, (vis[k] >> lane) & 1u, dmk[k], used, thr, cur, anyfeas);
-            sc[k] = fz[k] ? (sc2[k].x + sc2[k].y) * (0.25f * LOG2E) : -INFINITY;
+            fz[k] = feasible<ENV>(lane + 32 * k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
+            float dot = (sc2[k].x + sc2[k].y) + FK[k];
+            if (ENV == CO_ENV_CVRP) dot = fmaf(rem, WK[k], dot);
+            sc[k] = fz[k] ? dot * (0.25f * LOG2E) : -INFINITY;
             m = fmaxf(m, sc[k]);
           }
           m = funkey(__reduce_max_sync(FULL, fkey(m)));
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         __syncthreads();  // B1: heads complete
 
         // ---------------- pointer logits + tanh clip + mask: thread (nL, part)
-        const bool fzL = feasible<ENV>(nL, vis_bit(nL), dL, used, thr, cur, anyfeas);
+        const bool fzL = feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
         float z;
         {
           const float4* ov = reinterpret_cast<const float4*>(sm.o + part * OPAD);
@@ -396,6 +408,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           if (tid < E) sm.qfix[tid] = (A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f) +
                                       __ldg(crow + (size_t)a * CW + 3 * E + tid);
           __syncthreads();
+          head_dot(sm.qfix, FK);
         }
       }
 

@@ -124,7 +124,7 @@ class AttentionModelEncoder(nn.Module):
 
     #: instances per forward chunk when no autograd graph is needed (bounds the FFN-hidden
     #: activation to chunk * N * 512 floats; exact because eval-mode norms are per element)
-    inference_chunk = 8192
+    inference_chunk = 65536
     #: "tf32x3": Linear layers run on the hand-written tcgen05 3xTF32 GEMM (fp32-class accuracy)
     #: with bias / ReLU / skip connection / eval-mode BatchNorm folded into its epilogue -- CUDA,
     #: no-grad, eval only; "cublas": stock nn.Linear (strict fp32), always used under autograd.
@@ -144,18 +144,42 @@ class AttentionModelEncoder(nn.Module):
         return out, init_h
 
     # ------------------------------------------------------------------ tensor-core inference path
-    def _split(self, w):
-        """(hi, lo) tf32 split of a weight, cached until the parameter is modified."""
+    def _split(self, w, k_slices: int = 1):
+        """(hi, lo) tf32 split of a weight, cached until the parameter is modified.  With
+        `k_slices` > 1 returns a list of per-K-slice contiguous (hi, lo) pairs (split-K)."""
         from . import native
 
         cache = self.__dict__.setdefault("_split_cache", {})
-        key = id(w)
+        key = (id(w), k_slices)
         ver = (w._version, w.data_ptr())
         hit = cache.get(key)
         if hit is None or hit[0] != ver:
-            hit = (ver, native.split_tf32(w))
+            if k_slices == 1:
+                val = native.split_tf32(w)
+            else:
+                ks = w.shape[1] // k_slices
+                val = [native.split_tf32(w[:, i * ks:(i + 1) * ks].contiguous()) for i in range(k_slices)]
+            hit = (ver, val)
             cache[key] = hit
         return hit[1]
+
+    def _linear_splitk(self, x, lin, residual, aff):
+        """out = affine(x @ W^T + b + residual) for K = k*128 through the W-stationary K=128 pipeline:
+        k passes, each accumulating onto the previous partial via the epilogue's residual operand."""
+        from . import native
+
+        K = lin.weight.shape[1]
+        n = K // 128
+        parts = self._split(lin.weight, n)
+        acc = None
+        for i, (hi, lo) in enumerate(parts):
+            last = i == n - 1
+            a = x[:, i * 128:(i + 1) * 128]
+            res = residual if i == 0 else acc
+            acc = native.gemm_tf32x3(a, hi, lo, out=acc if i > 0 else None, bias=lin.bias if i == 0 else None,
+                                     residual=res, scale=aff[0] if (last and aff is not None) else None,
+                                     shift=aff[1] if (last and aff is not None) else None)
+        return acc
 
     @staticmethod
     def _bn_affine(norm):
@@ -193,10 +217,13 @@ class AttentionModelEncoder(nn.Module):
             for lin in lins[:-1]:
                 f = native.gemm_tf32x3(f, *self._split(lin.weight), bias=lin.bias, relu=True)
             aff = self._bn_affine(norm2)
-            if aff is not None:
-                h = native.gemm_tf32x3(f, *self._split(lins[-1].weight), bias=lins[-1].bias, residual=h,
-                                       scale=aff[0], shift=aff[1])
+            last = lins[-1]
+            if last.weight.shape[1] % 128 == 0 and last.weight.shape[1] > 128:
+                h = self._linear_splitk(f, last, h, aff)
+            elif aff is not None:
+                h = native.gemm_tf32x3(f, *self._split(last.weight), bias=last.bias, residual=h, scale=aff[0], shift=aff[1])
             else:
-                h = native.gemm_tf32x3(f, *self._split(lins[-1].weight), bias=lins[-1].bias, residual=h)
+                h = native.gemm_tf32x3(f, *self._split(last.weight), bias=last.bias, residual=h)
+            if aff is None:
                 h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()
         return h.view(B, N, E)
