@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       int cur = (ENV == CO_ENV_TSP) ? NS : 0;  // NS -> zero row: step-0 placeholder context
       int prev = 0, first = 0, t = 0, dstep = 0, optr = 0, nvis = 0;
       float used = 0.f, dist = 0.f;
-      bool anyfeas = false, done = false;
+      bool anyfeas = false, done = false, depot_seen = false;
       __syncthreads();  // previous trajectory finished with qfix / ll_acc
       if (tid < E) {
         float g = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;
@@ -243,8 +243,11 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           if (t == 0) first = a;
         } else {
           used = (used + sm.dem[a == 0 ? 1 : a]) * (a != 0 ? 1.0f : 0.0f);  // cvrp/env.py:70-76
-          // every thread records the visit itself, so its own later reads see it without a barrier
-          nvis += sm.vis_s[a] ? 0 : 1;
+          // distinct nodes visited: a customer is new by construction (masked once visited), the depot
+          // only on its first visit.  Every thread records the visit itself (all write the same value),
+          // so its own later reads of vis_s see it without a barrier.
+          nvis += (a != 0 || !depot_seen) ? 1 : 0;
+          depot_seen = depot_seen || (a == 0);
           sm.vis_s[a] = 1;
           // depot rule (cvrp/env.py:134): any unvisited customer that still fits <=> the
           // unvisited customer of least demand fits (fp32 add is monotone in the demand)
