@@ -73,7 +73,9 @@ __device__ __forceinline__ float philox_exp1(uint64_t seed, uint64_t offset, uin
   uint4 c = make_uint4(traj, step, node, (uint32_t)offset);
   uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
   uint4 r = philox4x32_10(c, k);
-  float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1): q never 0
+  // 23 random bits + 0.5: every value is exactly representable in fp32, so u in [2^-24, 1 - 2^-24]
+  // and q = -log(u) is finite and > 0 (with 24 bits, 16777215.5 would round up to 2^24 -> u = 1 -> q = 0)
+  float u = ((float)(r.x >> 9) + 0.5f) * (1.0f / 8388608.0f);
   return -logf(u);
 }
 

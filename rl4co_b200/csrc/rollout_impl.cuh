@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         {
           const float ex = (part == 0) ? ex2((z - Zb) * LOG2E) : 0.f;  // exp(z - Zb) in (0,1]; 0 if masked
           const float wsum = warp_sum(ex);
-          const float keyf = (MODE == CO_MODE_SAMPLE) ? ((part == 0) ? z + gum : -INFINITY) : z;
+          const float keyf = (MODE == CO_MODE_SAMPLE) ? ((part == 0 && fzL) ? z + gum : -INFINITY) : z;
           const unsigned key = fkey(keyf);
           const unsigned wkey = __reduce_max_sync(FULL, key);
           const unsigned vote = __ballot_sync(FULL, key == wkey);

@@ -402,6 +402,20 @@ def test_sampling_philox_is_valid_and_seeded(dev):
     assert (a["log_likelihood"] < 0).all()
 
 
+def test_sampling_never_selects_masked_nodes_at_scale(dev):
+    """2.4e7 in-kernel Exp(1) draws: regression for the u == 1 -> q == 0 -> NaN-key bug (prob 2^-24)."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(0)
+    env = get_env("cvrp", generator_params=dict(num_loc=100), check_solution=True)
+    pol = FusedAttentionModelPolicy(env_name="cvrp", num_encoder_layers=1).to(dev).eval()
+    with torch.inference_mode():
+        td = env.reset(env.generator(2048).to(dev))
+        for seed in (5, 6):
+            pol(td, env, decode_type="sampling", seed=seed)  # check_solution=True raises on an invalid tour
+
+
 def test_tour_length_properties_full_size(dev):
     """BASELINE-size property checks: reward kernel == in-kernel incremental reward; rotation
     invariance of TSP tours; all tours valid."""
