@@ -100,6 +100,22 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, float* stage,
 #pragma unroll 1
     for (int c2 = 0; c2 < cc_count; ++c2) {
       const int cc = cc_begin + c2;
+      // operands of the fused epilogue first: their latency hides behind the TMEM read + transpose
+      const int n = n0 + cc * 32 + 4 * v;
+      const bool n_ok = n < g.Nout;
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bs;
+      if (n_ok && g.bias) bs = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if (n_ok && g.scale) { sc4 = __ldg(reinterpret_cast<const float4*>(g.scale + n)); sh4 = __ldg(reinterpret_cast<const float4*>(g.shift + n)); }
+      float4 res[8];
+      if (g.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + 32 * wq + 4 * i + rr;
+          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          // plain (coherent) load: the residual may alias C (in-place accumulation across split-K passes)
+          if (row < g.M && n_ok) res[i] = *reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n);
+        }
+      }
       uint32_t r[32];
       const uint32_t taddr = tmem_d + ((uint32_t)(32 * wq) << 16) + cc * 32;
       asm volatile(
@@ -116,11 +132,6 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, float* stage,
       for (int u = 0; u < 8; ++u)  // thread = row `lane`: chunk u stored at u ^ (lane & 7)
         *reinterpret_cast<uint4*>(stage + lane * 32 + ((u ^ (lane & 7)) << 2)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
       __syncwarp();
-      const int n = n0 + cc * 32 + 4 * v;
-      const bool n_ok = n < g.Nout;
-      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = bs;
-      if (n_ok && g.bias) bs = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-      if (n_ok && g.scale) { sc4 = __ldg(reinterpret_cast<const float4*>(g.scale + n)); sh4 = __ldg(reinterpret_cast<const float4*>(g.shift + n)); }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int lrow = 4 * i + rr;
@@ -128,10 +139,7 @@ __device__ __forceinline__ void epilogue_chunks(const GemmArgs& g, float* stage,
         float4 o = *reinterpret_cast<const float4*>(stage + lrow * 32 + ((v ^ (lrow & 7)) << 2));
         if (row < g.M && n_ok) {
           o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
-          if (g.residual) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.ldr + n));
-            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-          }
+          if (g.residual) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
           if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           if (g.scale) { o.x = fmaf(o.x, sc4.x, sh4.x); o.y = fmaf(o.y, sc4.y, sh4.y); o.z = fmaf(o.z, sc4.z, sh4.z); o.w = fmaf(o.w, sc4.w, sh4.w); }
           *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
