@@ -10,6 +10,8 @@
 // softmax: scores via packed FFMA2, one rescale per block, ex2.approx, value accumulation via
 // FFMA2.  No N x N matrix ever exists in memory: HBM traffic = read qkv once + write out once
 // (N*(384+128)*4 B per instance).
+#include <stdlib.h>
+
 #include "co_common.cuh"
 
 namespace co {
@@ -22,19 +24,22 @@ __device__ __forceinline__ float ex2_(float x) {
   return y;
 }
 
-template <int ROWS>
-__global__ void __launch_bounds__(256, ROWS == 4 ? 1 : 2) encoder_mha_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                                             int B, int N) {
+// WPH warps per head: warp w -> head w % 8, row group w / 8; lane l owns query rows
+// 32 * (rowgroup * ROWS + r) + l.  <ROWS=2, WPH=2> (512 threads, <= 128 registers) doubles the resident
+// warps for N > 64 compared with <4, 1>: the kernel is latency-bound, not FMA-bound.
+template <int ROWS, int WPH>
+__global__ void __launch_bounds__(256 * WPH, (ROWS * WPH == 4) ? 1 : 2) encoder_mha_kernel(const float* __restrict__ qkv,
+                                                                                           float* __restrict__ out, int B, int N) {
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;             // [N][128]
   float* Vs = sm + N * E;     // [N][128]
-  const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, h = (tid >> 5) & 7, rowbase = 32 * ROWS * (tid >> 8);
   constexpr float QSCALE = 0.25f * 1.4426950408889634f;  // 1/sqrt(16) * log2(e): scores in log2 units
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float* base = qkv + (size_t)b * N * 3 * E;
     __syncthreads();  // previous instance done with Ks / Vs
-    for (int idx = tid; idx < N * 32; idx += 256) {
+    for (int idx = tid; idx < N * 32; idx += 256 * WPH) {
       const int n = idx >> 5, c = idx & 31;
       reinterpret_cast<float4*>(Ks + n * E)[c] = __ldg(reinterpret_cast<const float4*>(base + (size_t)n * 3 * E + E) + c);
       reinterpret_cast<float4*>(Vs + n * E)[c] = __ldg(reinterpret_cast<const float4*>(base + (size_t)n * 3 * E + 2 * E) + c);
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(256, ROWS == 4 ? 1 : 2) encoder_mha_kernel(con
     float m[ROWS], l[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int row = lane + 32 * r;
+      const int row = rowbase + lane + 32 * r;
       m[r] = -INFINITY; l[r] = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(256, ROWS == 4 ? 1 : 2) encoder_mha_kernel(con
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int row = lane + 32 * r;
+      const int row = rowbase + lane + 32 * r;
       if (row < N) {
         const float inv = 1.0f / l[r];
         float4* dst = reinterpret_cast<float4*>(out + ((size_t)b * N + row) * E + h * D);
@@ -121,9 +126,9 @@ __global__ void __launch_bounds__(256, ROWS == 4 ? 1 : 2) encoder_mha_kernel(con
   }
 }
 
-template <int ROWS>
+template <int ROWS, int WPH>
 static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t st) {
-  auto kern = encoder_mha_kernel<ROWS>;
+  auto kern = encoder_mha_kernel<ROWS, WPH>;
   const size_t smem = (size_t)2 * N * E * sizeof(float);
   static int max_smem_set = 0, ctas = 1;
   if ((int)smem > max_smem_set) {
@@ -131,10 +136,10 @@ static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t s
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_encoder_mha: smem attribute: %s", cudaGetErrorString(e));
     max_smem_set = (int)smem;
   }
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256 * WPH, smem);
   int grid = device_info().sm_count * (ctas < 1 ? 1 : ctas);
   if (grid > B) grid = B;
-  kern<<<grid, 256, smem, st>>>(qkv, out, B, N);
+  kern<<<grid, 256 * WPH, smem, st>>>(qkv, out, B, N);
   return check_launch("co_encoder_mha");
 }
 
@@ -149,7 +154,9 @@ extern "C" int co_encoder_mha(const float* qkv, float* out, int B, int N, void* 
   if (((uintptr_t)qkv | (uintptr_t)out) & 15) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: pointers must be 16-byte aligned%s");
   if (B == 0) return CO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 32) return launch_mha<1>(qkv, out, B, N, st);
-  if (N <= 64) return launch_mha<2>(qkv, out, B, N, st);
-  return launch_mha<4>(qkv, out, B, N, st);
+  static const int variant = getenv("CO_MHA_VARIANT") ? atoi(getenv("CO_MHA_VARIANT")) : 1;
+  if (N <= 32) return launch_mha<1, 1>(qkv, out, B, N, st);
+  if (N <= 64) return launch_mha<2, 1>(qkv, out, B, N, st);
+  if (variant == 0) return launch_mha<4, 1>(qkv, out, B, N, st);
+  return launch_mha<2, 2>(qkv, out, B, N, st);
 }
