@@ -154,7 +154,7 @@ extern "C" int co_encoder_mha(const float* qkv, float* out, int B, int N, void* 
   if (((uintptr_t)qkv | (uintptr_t)out) & 15) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: pointers must be 16-byte aligned%s");
   if (B == 0) return CO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int variant = getenv("CO_MHA_VARIANT") ? atoi(getenv("CO_MHA_VARIANT")) : 1;
+  static const int variant = getenv("CO_MHA_VARIANT") ? atoi(getenv("CO_MHA_VARIANT")) : 0;
   if (N <= 32) return launch_mha<1, 1>(qkv, out, B, N, st);
   if (N <= 64) return launch_mha<2, 1>(qkv, out, B, N, st);
   if (variant == 0) return launch_mha<4, 1>(qkv, out, B, N, st);

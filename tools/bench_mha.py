@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rl4co_b200 import native
-B, N = 65536, 100
+B, N = int(os.environ.get('B', 65536)), 100
 qkv = torch.randn(B * N, 384, device="cuda")
 def t(fn, n=3):
     fn(); torch.cuda.synchronize()
