@@ -23,9 +23,9 @@
 //   * the log-softmax uses the tanh-clip bound as its fixed offset (z <= clip/T), so per-warp
 //     partial sums add up without any exp in the cross-warp combine; arg-max is REDUX.MAX +
 //     ballot; sampling is arg-max of z - log q (Gumbel form of torch.multinomial's p/q);
-//   * the visited set is a bitmask in registers (SPL x uint32) replicated in every thread;
-//     capacity / current node are replicated scalars; the CVRP depot rule uses a pointer into
-//     the demand-sorted customer list instead of a block-wide OR;
+//   * each thread keeps only the visited bits it needs (its glimpse slots + its logits node);
+//     capacity / current node are replicated scalars; the CVRP depot rule uses a register bitmask
+//     over demand ranks (ffs = unvisited customer of least demand) instead of a block-wide OR;
 //   * exactly two block barriers per node selection; no state in HBM.
 // HBM traffic per instance = one read of its cache rows + T*(8+4) B of outputs.
 #pragma once
@@ -62,7 +62,7 @@ struct Smem {
   float dem[32 * SPL];
   float2 loc[32 * SPL];
   unsigned char order[32 * SPL];    // cvrp: customers sorted by demand (ascending)
-  unsigned char vis_s[32 * SPL];    // cvrp: visited flags (every thread writes the same value itself)
+  unsigned char rank_of[32 * SPL];  // cvrp: demand rank of each customer (inverse of `order`)
   float ll_acc;
 };
 
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           rank += (dm < d || (dm == d && m < tid)) ? 1 : 0;
         }
         sm.order[rank] = (unsigned char)tid;
+        sm.rank_of[tid] = (unsigned char)rank;
       }
       __syncthreads();
     }
@@ -216,9 +217,16 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       uint32_t mybits = (nL >= N) ? 0x100u : 0u;
 #pragma unroll
       for (int k = 0; k < SPL; ++k) mybits |= (lane + 32 * k >= N) ? (1u << k) : 0u;
-      if (ENV == CO_ENV_CVRP && tid < NS) sm.vis_s[tid] = 0;  // ordered before first use by the barrier below
       int cur = (ENV == CO_ENV_TSP) ? NS : 0;  // NS -> zero row: step-0 placeholder context
-      int prev = 0, first = 0, t = 0, dstep = 0, optr = 0, nvis = 0;
+      int prev = 0, first = 0, t = 0, dstep = 0, nvis = 0;
+      // cvrp: visited customers as a bitmask over demand RANKS (bits >= #customers pre-set), so the
+      // unvisited customer of least demand is ffs(~mask): registers only, nothing shared is written
+      uint32_t rmask[SPL];
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) {
+        const int lo = 32 * k, nc = N - 1;
+        rmask[k] = (nc >= lo + 32) ? 0u : (nc <= lo ? 0xffffffffu : (0xffffffffu << (nc - lo)));
+      }
       float used = 0.f, dist = 0.f;
       bool anyfeas = false, done = false, depot_seen = false;
       __syncthreads();  // previous trajectory finished with qfix / ll_acc
@@ -244,16 +252,23 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         } else {
           used = (used + sm.dem[a == 0 ? 1 : a]) * (a != 0 ? 1.0f : 0.0f);  // cvrp/env.py:70-76
           // distinct nodes visited: a customer is new by construction (masked once visited), the depot
-          // only on its first visit.  Every thread records the visit itself (all write the same value),
-          // so its own later reads of vis_s see it without a barrier.
+          // only on its first visit
           nvis += (a != 0 || !depot_seen) ? 1 : 0;
           depot_seen = depot_seen || (a == 0);
-          sm.vis_s[a] = 1;
-          // depot rule (cvrp/env.py:134): any unvisited customer that still fits <=> the
-          // unvisited customer of least demand fits (fp32 add is monotone in the demand)
-          const int ncust = N - 1;
-          while (optr < ncust && sm.vis_s[sm.order[optr]]) ++optr;
-          anyfeas = (optr < ncust) && !((sm.dem[sm.order[optr < ncust ? optr : 0]] + used) > thr);
+          if (a != 0) {
+            const int r = sm.rank_of[a];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) rmask[k] |= ((r >> 5) == k) ? (1u << (r & 31)) : 0u;
+          }
+          // depot rule (cvrp/env.py:134): any unvisited customer that still fits <=> the unvisited
+          // customer of least demand fits (fp32 add is monotone in the demand)
+          int pmin = NS;
+#pragma unroll
+          for (int k = SPL - 1; k >= 0; --k) {
+            const uint32_t z = ~rmask[k];
+            if (z) pmin = 32 * k + __ffs(z) - 1;
+          }
+          anyfeas = (pmin < N - 1) && !((sm.dem[sm.order[pmin < N - 1 ? pmin : 0]] + used) > thr);
         }
         prev = a; cur = a; ++t;
         done = (ENV == CO_ENV_TSP) ? (t >= N) : (nvis >= N);  // cvrp: all nodes incl. the depot visited

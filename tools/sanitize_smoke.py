@@ -1,0 +1,33 @@
+"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from rl4co_b200 import native
+from rl4co_b200.envs import get_env
+from rl4co_b200.policy import FusedAttentionModelPolicy
+from rl4co_b200.reinforce import pomo_step
+
+dev = torch.device("cuda:0")
+CASES = (("tsp", 20), ("cvrp", 20), ("tsp", 50), ("cvrp", 100), ("tsp", 100))
+if os.environ.get("SAN_ONLY"):
+    CASES = tuple(c for c in CASES if c[0] == os.environ["SAN_ONLY"])
+for env_name, n in CASES:
+    torch.manual_seed(0)
+    env = get_env(env_name, generator_params=dict(num_loc=n), check_solution=True)
+    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=1).to(dev).eval()
+    with torch.inference_mode():
+        td = env.reset(env.generator(300).to(dev))
+        for dt, kw in (("greedy", {}), ("sampling", {"seed": 1}), ("multistart_greedy", {"num_starts": 3})):
+            out = pol(td, env, decode_type=dt, **kw)
+        out = pol(td, env, decode_type="greedy", fused_rollout=False)   # stepping kernels
+        pol(td, env, actions=out["actions"])                             # evaluate mode
+    print(env_name, n, "ok", out["reward"].mean().item())
+# large-M GEMM path (pipe) + generic
+a = torch.randn(20000, 128, device=dev); w = torch.randn(384, 128, device=dev)
+hi, lo = native.split_tf32(w)
+native.gemm_tf32x3(a, hi, lo, bias=torch.randn(384, device=dev), relu=True)
+a = torch.randn(300, 512, device=dev); w = torch.randn(128, 512, device=dev)
+hi, lo = native.split_tf32(w)
+native.gemm_tf32x3(a, hi, lo, residual=torch.randn(300, 128, device=dev))
+torch.cuda.synchronize()
+print("gemm ok")
