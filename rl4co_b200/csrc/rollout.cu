@@ -1,10 +1,14 @@
 // C-ABI entry of the persistent rollout (argument validation + dispatch); kernels live in
 // rollout_impl.cuh, instantiated in rollout_tsp.cu / rollout_cvrp.cu.
+#include <stdlib.h>
+
 #include "co_common.cuh"
 
 namespace co {
 int rollout_tsp(const co_rollout_args& A, cudaStream_t st);
 int rollout_cvrp(const co_rollout_args& A, cudaStream_t st);
+int rollout_ms_tsp(const co_rollout_args& A, cudaStream_t st);   // query-batched (num_starts > 1)
+int rollout_ms_cvrp(const co_rollout_args& A, cudaStream_t st);
 }  // namespace co
 
 using namespace co;
@@ -32,14 +36,17 @@ extern "C" int co_rollout(const co_rollout_args* args, void* stream) {
   if ((A.flags & CO_ROLLOUT_FORCED_START) && A.num_loc < 1) return fail(CO_ERR_BAD_ARG, "co_rollout: num_loc required for forced starts%s");
   if (A.B_inst == 0) return CO_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // S > 1 trajectories per instance: the query-batched kernel advances 4 of them per pass
+  static const bool use_ms = !(getenv("CO_ROLLOUT_MS") && atoi(getenv("CO_ROLLOUT_MS")) == 0);
+  const bool ms = use_ms && A.num_starts > 1;
   if (A.env_kind == CO_ENV_TSP) {
     if (!A.q_placeholder) return fail(CO_ERR_BAD_ARG, "co_rollout: q_placeholder required for tsp%s");
     if (A.T_max < A.N) return fail(CO_ERR_BAD_ARG, "co_rollout: T_max < N%s");
-    return rollout_tsp(A, st);
+    return ms ? rollout_ms_tsp(A, st) : rollout_tsp(A, st);
   }
   if (A.env_kind == CO_ENV_CVRP) {
     if (!A.demand || !A.w_capacity) return fail(CO_ERR_BAD_ARG, "co_rollout: demand / w_capacity required for cvrp%s");
-    return rollout_cvrp(A, st);
+    return ms ? rollout_ms_cvrp(A, st) : rollout_cvrp(A, st);
   }
   return fail(CO_ERR_BAD_ARG, "co_rollout: unknown env kind%s");
 }

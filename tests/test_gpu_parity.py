@@ -296,6 +296,25 @@ def test_rollout_multistart_vs_golden(golden, dev, name, graph_ctx, gemm):
     assert same.all() if gemm == "cublas" else same.float().mean() >= 0.75
 
 
+@pytest.mark.parametrize("name", AM_FIX)
+def test_rollout_multisample_query_batched(golden, dev, name):
+    """num_samples > 1 without forced start nodes (decoding.py multisample): S trajectories per
+    instance through the query-batched kernel, every column decoded (incl. the TSP placeholder step)."""
+    g = golden(name)
+    env_name = env_of(name)
+    pol = make_policy(env_name, g.weights(), dev)
+    S = 6  # not a multiple of the kernel's 4 trajectories per pass: exercises the tail group
+    out, _, _ = fused_rollout(pol, env_name, g, dev, "sampling", num_samples=S, seed=9)
+    B = g["h"].shape[0]
+    assert out["actions"].shape[0] == S * B
+    inst = {k: O.batchify(v, S) for k, v in g.inst().items()}
+    with torch.inference_mode():
+        ref = O.rollout(g.weights(), env_name, inst, O.batchify(g["h"], S), actions=out["actions"].cpu(), faithful_copies=False)
+    torch.testing.assert_close(out["log_likelihood"].cpu(), ref["logprobs"], rtol=RTOL, atol=ATOL_LP)
+    torch.testing.assert_close(out["reward"].cpu(), ref["reward"], rtol=RTOL, atol=1e-6)
+    assert not torch.equal(out["actions"][:B], out["actions"][B:2 * B])  # samples differ across s
+
+
 @pytest.mark.parametrize("name", ["am_tsp20", "am_cvrp20"])
 def test_stepping_path_matches_fused_path(golden, dev, name):
     g = golden(name)
