@@ -3,14 +3,16 @@
 // same way through `unbatchify`), so this variant advances Q = 4 trajectories per pass.
 //
 // Same structure and numerics as rollout_impl.cuh (read that header first); differences:
-//   * every phase loops over the Q trajectories of the group before the block barrier, so the two
-//     barriers, the serial dependency chain and the register-resident K / V loads are amortised
-//     over Q node selections (the single-trajectory kernel is latency-bound at 37 % issue use);
+//   * every phase handles the Q trajectories of the group before the block barrier, written
+//     stage-major in straight-line code so that their independent instruction streams interleave
+//     (a warp issues in order: a per-trajectory loop would serialise the chains and gain nothing --
+//     measured); the two barriers and the serial REDUX / MUFU / shuffle / LDS latencies are thereby
+//     amortised over Q node selections (the single-trajectory kernel is latency-bound at 37 % issue use);
 //   * the folded logit key lives in shared memory (padded rows, conflict-free LDS.128) instead of
 //     registers -- it is read once per pass and reused by the Q queries -- which frees the
 //     registers for the per-trajectory state and accumulators;
-//   * trajectories that are done (CVRP: variable length) drop out of the phases; the group ends when
-//     all of its trajectories are done.
+//   * trajectories that are done (CVRP: variable length) are still computed but their results are
+//     discarded by predication; the group ends when all of its trajectories are done.
 // Layout of results is unchanged: row j = s * B + b (start-major, rl4co/utils/ops.py:10-29).
 #pragma once
 #include "rollout_impl.cuh"
@@ -228,69 +230,97 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
       for (int j = 0; j < Q; ++j) head_dot(sm.qfix[j], FK[j]);
 
       while (!(fin[0] && fin[1] && fin[2] && fin[3])) {
-        // ---------------- glimpse, per trajectory (warp h = head h)
+        // Every phase is written stage-major over the trajectories in straight-line code (no
+        // per-trajectory branches): a warp issues in order, so only interleaved independent
+        // instruction streams hide the REDUX / MUFU / shuffle / LDS latencies of each chain.
+        // Finished trajectories are computed too (their results are discarded by predication).
+        // ---------------- glimpse (warp h = head h), two trajectories at a time (two transpose tiles)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) {
-          if (fin[j]) continue;
-          const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur[j] * E + h * D);
-          const float rem = cap - used[j];
-          float2 sc2[SPL];
+        for (int jp = 0; jp < Q; jp += 2) {
+          float sc[2][SPL], m[2], esum[2];
+          uint32_t fzb[2];
+          // stage A: scores of both trajectories, feasibility, row max
 #pragma unroll
-          for (int k = 0; k < SPL; ++k) sc2[k] = make_float2(0.f, 0.f);
+          for (int u = 0; u < 2; ++u) {
+            const int j = jp + u;
+            const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur[j] * E + h * D);
+            const float rem = cap - used[j];
+            float2 sc2[SPL];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 p = pr[c];
+            for (int k = 0; k < SPL; ++k) sc2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 p = pr[c];
+#pragma unroll
+              for (int k = 0; k < SPL; ++k) {
+                sc2[k] = ffma2(make_float2(p.x, p.y), Kr[k][2 * c], sc2[k]);
+                sc2[k] = ffma2(make_float2(p.z, p.w), Kr[k][2 * c + 1], sc2[k]);
+              }
+            }
+            float mm = -INFINITY;
+            fzb[u] = 0;
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
-              sc2[k] = ffma2(make_float2(p.x, p.y), Kr[k][2 * c], sc2[k]);
-              sc2[k] = ffma2(make_float2(p.z, p.w), Kr[k][2 * c + 1], sc2[k]);
+              const bool f = feasible<ENV>(lane + 32 * k, (mybits[j] >> k) & 1u, dmk[k], used[j], thr, cur[j], anyfeas[j]);
+              fzb[u] |= f ? (1u << k) : 0u;
+              float dot = (sc2[k].x + sc2[k].y) + FK[j][k];
+              if (ENV == CO_ENV_CVRP) dot = fmaf(rem, WK[k], dot);
+              sc[u][k] = f ? dot * (0.25f * LOG2E) : -INFINITY;
+              mm = fmaxf(mm, sc[u][k]);
             }
+            m[u] = mm;
           }
-          float sc[SPL], m = -INFINITY;
-          bool fz[SPL];
+          const unsigned mk0 = __reduce_max_sync(FULL, fkey(m[0])), mk1 = __reduce_max_sync(FULL, fkey(m[1]));
+          m[0] = funkey(mk0); m[1] = funkey(mk1);
+          // stage B: exp, value accumulation, partial outputs to the trajectory's tile
 #pragma unroll
-          for (int k = 0; k < SPL; ++k) {
-            fz[k] = feasible<ENV>(lane + 32 * k, (mybits[j] >> k) & 1u, dmk[k], used[j], thr, cur[j], anyfeas[j]);
-            float dot = (sc2[k].x + sc2[k].y) + FK[j][k];
-            if (ENV == CO_ENV_CVRP) dot = fmaf(rem, WK[k], dot);
-            sc[k] = fz[k] ? dot * (0.25f * LOG2E) : -INFINITY;
-            m = fmaxf(m, sc[k]);
+          for (int u = 0; u < 2; ++u) {
+            float2 acc[8];
+            float es = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+              const float e = ((fzb[u] >> k) & 1u) ? ex2(sc[u][k] - m[u]) : 0.f;
+              es += e;
+              const float2 e2 = make_float2(e, e);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[c] = ffma2(e2, Vr[k][c], acc[c]);
+            }
+            esum[u] = es;
+            float4* trow = reinterpret_cast<float4*>(sm.tile[h][u] + lane * TILE_LD);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) trow[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
           }
-          m = funkey(__reduce_max_sync(FULL, fkey(m)));
-          float2 acc[8];
-          float esum = 0.f;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int k = 0; k < SPL; ++k) {
-            const float e = fz[k] ? ex2(sc[k] - m) : 0.f;
-            esum += e;
-            const float2 e2 = make_float2(e, e);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[c] = ffma2(e2, Vr[k][c], acc[c]);
+          for (int off = 16; off > 0; off >>= 1) {  // both row sums, level by level
+            const float t0 = __shfl_xor_sync(FULL, esum[0], off), t1 = __shfl_xor_sync(FULL, esum[1], off);
+            esum[0] += t0; esum[1] += t1;
           }
-          float* tile = sm.tile[h][j & 1];
-          float4* trow = reinterpret_cast<float4*>(tile + lane * TILE_LD);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) trow[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
-          esum = warp_sum(esum);
           __syncwarp();
+          // stage C: lane sums through the transposed tiles, normalise, publish heads
           const int d = lane & 15, half = lane >> 4;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float r2[2];
 #pragma unroll
-          for (int r = 0; r < 16; r += 4) {
-            s0 += tile[(16 * half + ((r + 0 + 4 * half) & 15)) * TILE_LD + d];
-            s1 += tile[(16 * half + ((r + 1 + 4 * half) & 15)) * TILE_LD + d];
-            s2 += tile[(16 * half + ((r + 2 + 4 * half) & 15)) * TILE_LD + d];
-            s3 += tile[(16 * half + ((r + 3 + 4 * half) & 15)) * TILE_LD + d];
+          for (int u = 0; u < 2; ++u) {
+            const float* tile = sm.tile[h][u];
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; r += 4) {
+              s0 += tile[(16 * half + ((r + 0 + 4 * half) & 15)) * TILE_LD + d];
+              s1 += tile[(16 * half + ((r + 1 + 4 * half) & 15)) * TILE_LD + d];
+              s2 += tile[(16 * half + ((r + 2 + 4 * half) & 15)) * TILE_LD + d];
+              s3 += tile[(16 * half + ((r + 3 + 4 * half) & 15)) * TILE_LD + d];
+            }
+            r2[u] = (s0 + s1) + (s2 + s3);
           }
-          float r = (s0 + s1) + (s2 + s3);
-          r += __shfl_xor_sync(FULL, r, 16);
+          const float x0 = __shfl_xor_sync(FULL, r2[0], 16), x1 = __shfl_xor_sync(FULL, r2[1], 16);
           if (lane < 16) {
             const int e = h * D + d;
-            sm.o[j][e + 4 * (e / EPP)] = __fdividef(r, esum);
+            sm.o[jp][e + 4 * (e / EPP)] = __fdividef(r2[0] + x0, esum[0]);
+            sm.o[jp + 1][e + 4 * (e / EPP)] = __fdividef(r2[1] + x1, esum[1]);
           }
-          __syncwarp();  // tile (j & 1) is reused two trajectories later
+          __syncwarp();  // the two tiles are reused by the next pair
         }
         __syncthreads();  // B1: heads of all trajectories complete
 
@@ -306,40 +336,52 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
             const float4 l4 = lk[c];
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
-              if (fin[j]) continue;
               const float4 x = reinterpret_cast<const float4*>(sm.o[j] + part * OPAD)[c];
               pa[j] = ffma2(make_float2(x.x, x.y), make_float2(l4.x, l4.y), pa[j]);
               pb[j] = ffma2(make_float2(x.z, x.w), make_float2(l4.z, l4.w), pb[j]);
             }
           }
+          float pl[Q], keyf[Q], ex[Q];
+#pragma unroll
+          for (int j = 0; j < Q; ++j) pl[j] = (pa[j].x + pa[j].y) + (pb[j].x + pb[j].y);
+#pragma unroll
+          for (int off = PARTS / 2; off > 0; off >>= 1) {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) pl[j] += __shfl_xor_sync(FULL, pl[j], off);
+          }
 #pragma unroll
           for (int j = 0; j < Q; ++j) {
-            if (fin[j]) { z[j] = -INFINITY; continue; }
-            float p = (pa[j].x + pa[j].y) + (pb[j].x + pb[j].y);
-#pragma unroll
-            for (int off = PARTS / 2; off > 0; off >>= 1) p += __shfl_xor_sync(FULL, p, off);
             const bool fzL = feasible<ENV>(nL, (mybits[j] >> 8) & 1u, dL, used[j], thr, cur[j], anyfeas[j]);
-            const float lg = tanhf(p * 0.08838834764831845f) * clip;
+            const float lg = tanhf(pl[j] * 0.08838834764831845f) * clip;
             z[j] = fzL ? lg * inv_temp : -INFINITY;
-            float keyf = z[j];
+            keyf[j] = z[j];
             if (MODE == CO_MODE_SAMPLE) {
-              keyf = -INFINITY;
+              keyf[j] = -INFINITY;
               if (part == 0 && fzL) {
                 const int traj = (g0 + j) * B_inst + b;
                 const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstep[j], nL)
-                                       : A.noise[((size_t)dstep[j] * B_traj + traj) * N + nL];
-                keyf = z[j] - logf(q);
+                                       : A.noise[((size_t)dstep[j] * B_traj + (traj < B_traj ? traj : 0)) * N + nL];
+                keyf[j] = z[j] - logf(q);
               }
             }
-            const float ex = (part == 0) ? ex2((z[j] - Zb) * LOG2E) : 0.f;
-            const float wsum = warp_sum(ex);
-            const unsigned key = fkey(keyf);
-            const unsigned wkey = __reduce_max_sync(FULL, key);
-            const unsigned vote = __ballot_sync(FULL, key == wkey);
-            if (lane == 0) {
-              sm.red_key[j][h] = wkey;
-              sm.red_idx[j][h] = h * NPW + (__ffs(vote) - 1) / PARTS;
-              sm.red_sum[j][h] = wsum;
+            ex[j] = (part == 0) ? ex2((z[j] - Zb) * LOG2E) : 0.f;
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {  // the Q partial sums, level by level
+#pragma unroll
+            for (int j = 0; j < Q; ++j) ex[j] += __shfl_xor_sync(FULL, ex[j], off);
+          }
+          unsigned wkey[Q], vote[Q];
+#pragma unroll
+          for (int j = 0; j < Q; ++j) wkey[j] = __reduce_max_sync(FULL, fkey(keyf[j]));
+#pragma unroll
+          for (int j = 0; j < Q; ++j) vote[j] = __ballot_sync(FULL, fkey(keyf[j]) == wkey[j]);
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+              sm.red_key[j][h] = wkey[j];
+              sm.red_idx[j][h] = h * NPW + (__ffs(vote[j]) - 1) / PARTS;
+              sm.red_sum[j][h] = ex[j];
             }
           }
         }
@@ -347,7 +389,6 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
         bool need_sync = false;
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-          if (fin[j]) continue;
           const int traj = (g0 + j) * B_inst + b;
           int a;
           float Ssum;
@@ -365,24 +406,26 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
             if (k1.z > bk) { bk = k1.z; a = i1.z; }
             if (k1.w > bk) { bk = k1.w; a = i1.w; }
           }
-          const int t = tstep[j];
-          if (MODE == CO_MODE_EVALUATE) {
-            const int forced = (int)A.forced_actions[(size_t)traj * T_max + t];
-            a = (forced < 0 || forced >= N) ? 0 : forced;
-          }
-          if (nL == a && part == 0) {
-            const float lpL = (z[j] - Zb) - lg2(Ssum) * LN2;
-            A.logp_out[(size_t)traj * T_max + t] = lpL;
-            sm.ll_acc[j] += lpL;
-          }
-          if (tid == 0) A.actions_out[(size_t)traj * T_max + t] = a;
-          const bool was_first = (ENV == CO_ENV_TSP) && (t == 0);
-          env_step(j, a);
-          ++dstep[j];
-          if (was_first) {  // multisample without forced start: context becomes [h_first ; h_cur]
-            if (tid < E) sm.qfix[j][tid] = (A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f) +
-                                           __ldg(crow + (size_t)a * CW + 3 * E + tid);
-            need_sync = true;
+          if (!fin[j]) {  // uniform across the block: the state is replicated
+            const int t = tstep[j];
+            if (MODE == CO_MODE_EVALUATE) {
+              const int forced = (int)A.forced_actions[(size_t)traj * T_max + t];
+              a = (forced < 0 || forced >= N) ? 0 : forced;
+            }
+            if (nL == a && part == 0) {
+              const float lpL = (z[j] - Zb) - lg2(Ssum) * LN2;
+              A.logp_out[(size_t)traj * T_max + t] = lpL;
+              sm.ll_acc[j] += lpL;
+            }
+            if (tid == 0) A.actions_out[(size_t)traj * T_max + t] = a;
+            const bool was_first = (ENV == CO_ENV_TSP) && (t == 0);
+            env_step(j, a);
+            ++dstep[j];
+            if (was_first) {  // multisample without forced start: context becomes [h_first ; h_cur]
+              if (tid < E) sm.qfix[j][tid] = (A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f) +
+                                             __ldg(crow + (size_t)a * CW + 3 * E + tid);
+              need_sync = true;
+            }
           }
         }
         if (need_sync) {  // uniform: tstep is replicated
