@@ -36,6 +36,17 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();
 
+// Function attributes (opt-in dynamic shared memory) are per device: remember them per device id so a
+// process that drives several GPUs configures each of them once.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool& flag() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return done[dev & 63];
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

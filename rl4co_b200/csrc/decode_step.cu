@@ -186,7 +186,8 @@ extern "C" int co_pointer_logits(int env_kind, const co_decoder_weights* w, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (env_kind == CO_ENV_TSP) {
     if (!first_node || !i || !w->w_placeholder) return fail(CO_ERR_BAD_ARG, "co_pointer_logits: tsp state missing%s");
-    static bool attr = false;
+    static PerDeviceOnce once;
+    bool& attr = once.flag();
     if (!attr && smem > 48 * 1024) {
       cudaFuncSetAttribute(pointer_logits_kernel<CO_ENV_TSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
@@ -196,7 +197,8 @@ extern "C" int co_pointer_logits(int env_kind, const co_decoder_weights* w, cons
         logit_key, action_mask, first_node, current_node, i, nullptr, nullptr, logits_out, B_inst, N, ld);
   } else if (env_kind == CO_ENV_CVRP) {
     if (!used_capacity || !vehicle_capacity) return fail(CO_ERR_BAD_ARG, "co_pointer_logits: cvrp state missing%s");
-    static bool attr = false;
+    static PerDeviceOnce once;
+    bool& attr = once.flag();
     if (!attr && smem > 48 * 1024) {
       cudaFuncSetAttribute(pointer_logits_kernel<CO_ENV_CVRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;

@@ -130,11 +130,13 @@ template <int ROWS, int WPH>
 static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t st) {
   auto kern = encoder_mha_kernel<ROWS, WPH>;
   const size_t smem = (size_t)2 * N * E * sizeof(float);
-  static int max_smem_set = 0, ctas = 1;
-  if ((int)smem > max_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static PerDeviceOnce once;
+  int ctas = 1;
+  bool& configured = once.flag();
+  if (!configured) {  // opt in to the largest footprint (N = 128) once per device
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * E * (int)sizeof(float));
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_encoder_mha: smem attribute: %s", cudaGetErrorString(e));
-    max_smem_set = (int)smem;
+    configured = true;
   }
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, 256 * WPH, smem);
   int grid = device_info().sm_count * (ctas < 1 ? 1 : ctas);

@@ -544,7 +544,8 @@ extern "C" int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo
   GemmArgs g{A, Whi, Wlo, C, bias, residual, scale, shift, M, Nout, K, lda, ldc, ldr, relu, (Nout + GN - 1) / GN};
   const long tiles = (long)((M + GM - 1) / GM) * g.n_tiles;
   if (tiles > 0x7fffffffL) return fail(CO_ERR_UNSUPPORTED, "co_gemm_tf32x3: too many tiles%s");
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TILE_BYTES);
     if (e == cudaSuccess)

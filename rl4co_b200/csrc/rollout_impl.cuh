@@ -451,8 +451,9 @@ template <int SPL, int ENV, int MODE>
 static int launch(const co_rollout_args& A, cudaStream_t st) {
   auto kern = rollout_kernel<SPL, ENV, MODE>;
   const size_t smem = sizeof(Smem<SPL>);
-  static bool configured = false;
+  static PerDeviceOnce once;
   static int ctas_per_sm = 1;
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_rollout: smem attribute: %s", cudaGetErrorString(e));

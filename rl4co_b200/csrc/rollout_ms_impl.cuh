@@ -464,7 +464,8 @@ template <int SPL, int ENV, int MODE>
 static int launch_ms(const co_rollout_args& A, cudaStream_t st) {
   auto kern = rollout_ms_kernel<SPL, ENV, MODE>;
   const size_t smem = sizeof(SmemMS<SPL>);
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CO_ERR_CUDA, "co_rollout(ms): smem attribute: %s", cudaGetErrorString(e));

@@ -163,6 +163,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device_of_first_tensor(fn):
+    """Run the wrapper with the CUDA device of its first tensor argument current, so the kernel is
+    enqueued on that device's current stream (a process may hold tensors on several GPUs)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return wrapper
+
+
 F32, I64, U8, I32 = torch.float32, torch.int64, torch.uint8, torch.int32
 
 
@@ -190,6 +208,7 @@ def rollout_max_nodes() -> int:
     return lib().co_rollout_max_nodes()
 
 
+@_on_device_of_first_tensor
 def tsp_step(action, mask_in, mask_out, first_node, current_node, i, done):
     B, N = mask_in.shape
     _check(lib().co_tsp_step(_ptr(action, I64, "action"), _bool_ptr(mask_in, "mask_in"), _bool_ptr(mask_out, "mask_out"),
@@ -197,6 +216,7 @@ def tsp_step(action, mask_in, mask_out, first_node, current_node, i, done):
                              _ptr(i, I64, "i"), _bool_ptr(done, "done"), B, N, _stream()), "co_tsp_step")
 
 
+@_on_device_of_first_tensor
 def cvrp_action_mask(demand, used, cap, visited, current_node, mask_out):
     B, N = visited.shape
     _check(lib().co_cvrp_action_mask(_ptr(demand, F32, "demand"), _ptr(used, F32, "used"), _ptr(cap, F32, "cap"),
@@ -204,6 +224,7 @@ def cvrp_action_mask(demand, used, cap, visited, current_node, mask_out):
                                      _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_cvrp_action_mask")
 
 
+@_on_device_of_first_tensor
 def cvrp_step(action, demand, cap, used_in, used_out, visited_in, visited_out, current_node, done, mask_out):
     B, N = visited_in.shape
     _check(lib().co_cvrp_step(_ptr(action, I64, "action"), _ptr(demand, F32, "demand"), _ptr(cap, F32, "cap"),
@@ -213,6 +234,7 @@ def cvrp_step(action, demand, cap, used_in, used_out, visited_in, visited_out, c
                               _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_cvrp_step")
 
 
+@_on_device_of_first_tensor
 def tour_length(locs, actions, with_depot: bool):
     B, T = actions.shape
     B_locs, N = locs.shape[0], locs.shape[1]
@@ -222,6 +244,7 @@ def tour_length(locs, actions, with_depot: bool):
     return reward
 
 
+@_on_device_of_first_tensor
 def check_tours(actions, N, demand=None, cap=None, B_inst=None) -> int:
     """Number of invalid tours (one host sync, like the reference's asserts)."""
     B, T = actions.shape
@@ -232,6 +255,7 @@ def check_tours(actions, N, demand=None, cap=None, B_inst=None) -> int:
     return int(bad.item())
 
 
+@_on_device_of_first_tensor
 def pointer_logits(env_name, weights: DecoderWeights, node_emb, graph_ctx, K, V, L, mask, first_node, current_node,
                    i, used, cap, B_traj, B_inst, N):
     """K / V / L: [B_inst, N, E] tensors, either contiguous or column-block views of one
@@ -251,6 +275,7 @@ def pointer_logits(env_name, weights: DecoderWeights, node_emb, graph_ctx, K, V,
     return logits
 
 
+@_on_device_of_first_tensor
 def select_action(logits, mask, mode, noise=None, action=None, tanh_clipping=10.0, temperature=1.0,
                   mask_logits=True, store_all_logp=False, seed=0, offset=0):
     B, N = logits.shape
@@ -265,6 +290,7 @@ def select_action(logits, mask, mode, noise=None, action=None, tanh_clipping=10.
     return action, logp, all_lp
 
 
+@_on_device_of_first_tensor
 def split_tf32(w: torch.Tensor):
     """(hi, lo) with hi = rna_tf32(w), lo = w - hi (both fp32) for co_gemm_tf32x3."""
     w = w.detach().contiguous()
@@ -274,6 +300,7 @@ def split_tf32(w: torch.Tensor):
     return hi, lo
 
 
+@_on_device_of_first_tensor
 def gemm_tf32x3(a, w_hi, w_lo, out=None, bias=None, residual=None, scale=None, shift=None, relu=False):
     """out[M, Nout] = epilogue(a[M, K] @ W[Nout, K]^T) on tcgen05 tensor cores (3xTF32).
     `a`, `out`, `residual` may be row-strided 2-D views (unit column stride)."""
@@ -292,6 +319,7 @@ def gemm_tf32x3(a, w_hi, w_lo, out=None, bias=None, residual=None, scale=None, s
     return out
 
 
+@_on_device_of_first_tensor
 def encoder_mha(qkv, B, N):
     """Self-attention core on the packed [B*N, 384] projection -> [B*N, 128]."""
     out = torch.empty(B * N, EMBED_DIM, dtype=F32, device=qkv.device)
@@ -299,11 +327,13 @@ def encoder_mha(qkv, B, N):
     return out
 
 
+@_on_device_of_first_tensor
 def reward_stats(reward, out2):
     _check(lib().co_reward_stats(_ptr(reward, F32, "reward"), _ptr(out2, torch.float64, "out2"), reward.numel(),
                                  _stream()), "co_reward_stats")
 
 
+@_on_device_of_first_tensor
 def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, locs, demand, vehicle_capacity,
             B_inst, N, num_starts=1, forced_start=False, num_loc=0, T_max=None, forced_actions=None, noise=None,
             tanh_clipping=10.0, temperature=1.0, seed=0, offset=0):
