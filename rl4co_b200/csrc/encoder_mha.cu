@@ -11,6 +11,7 @@
 // FFMA2.  No N x N matrix ever exists in memory: HBM traffic = read qkv once + write out once
 // (N*(384+128)*4 B per instance).
 #include <stdlib.h>
+#include <string.h>
 
 #include "co_common.cuh"
 
@@ -145,6 +146,9 @@ static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t s
   return check_launch("co_encoder_mha");
 }
 
+int launch_encoder_mha_tc(const float* qkv, float* out, int B, int N, cudaStream_t stream);   // encoder_mha_tc.cu
+int launch_encoder_mha_tc2(const float* qkv, float* out, int B, int N, cudaStream_t stream);               // encoder_mha_tc2.cu
+
 }  // namespace co
 
 using namespace co;
@@ -156,9 +160,13 @@ extern "C" int co_encoder_mha(const float* qkv, float* out, int B, int N, void* 
   if (((uintptr_t)qkv | (uintptr_t)out) & 15) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: pointers must be 16-byte aligned%s");
   if (B == 0) return CO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int variant = getenv("CO_MHA_VARIANT") ? atoi(getenv("CO_MHA_VARIANT")) : 0;
+  // CO_MHA_VARIANT = simt | tc | tc2 forces one kernel (read per call so tests can switch); default: tensor-core
+  // scores for N > 64, all-SIMT below (a 128 x 128 score tile is mostly padding there).
+  const char* ev = getenv("CO_MHA_VARIANT");
+  if (ev && !strcmp(ev, "tc2")) return launch_encoder_mha_tc2(qkv, out, B, N, st);
+  if (ev ? !strcmp(ev, "tc") : N > 64) return launch_encoder_mha_tc(qkv, out, B, N, st);
+  if (ev && strcmp(ev, "simt")) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: CO_MHA_VARIANT must be simt, tc or tc2%s");
   if (N <= 32) return launch_mha<1, 1>(qkv, out, B, N, st);
   if (N <= 64) return launch_mha<2, 1>(qkv, out, B, N, st);
-  if (variant == 0) return launch_mha<4, 1>(qkv, out, B, N, st);
-  return launch_mha<2, 2>(qkv, out, B, N, st);
+  return launch_mha<4, 1>(qkv, out, B, N, st);
 }

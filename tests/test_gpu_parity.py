@@ -392,16 +392,31 @@ def test_encoder_tensor_core_path_matches_fp32(dev, env_name, norm):
     torch.testing.assert_close(h_tc.cpu(), h_ref, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("B,N", [(3, 5), (7, 20), (64, 50), (9, 64), (33, 100), (5, 128), (2, 33)])
-def test_encoder_mha_kernel_vs_sdpa(dev, B, N):
+@pytest.mark.parametrize("variant", ["auto", "simt", "tc", "tc2"])
+@pytest.mark.parametrize("B,N", [(3, 5), (7, 20), (64, 50), (9, 64), (33, 100), (5, 128), (2, 33), (300, 97), (1, 1)])
+def test_encoder_mha_kernel_vs_sdpa(dev, monkeypatch, variant, B, N):
+    """Every attention kernel (all-SIMT, tcgen05 scores, tcgen05 scores + P.V) against float64 SDPA; B = 300 makes
+    the persistent CTAs loop over several instances (ring / phase wrap-around of the mbarrier pipelines)."""
     from rl4co_b200 import native
 
+    if variant == "auto":
+        monkeypatch.delenv("CO_MHA_VARIANT", raising=False)
+    else:
+        monkeypatch.setenv("CO_MHA_VARIANT", variant)
     torch.manual_seed(B * N)
     qkv = torch.randn(B * N, 384, device=dev) * 1.5
     out = native.encoder_mha(qkv, B, N)
     q, k, v = qkv.view(B, N, 3, 8, 16).permute(2, 0, 3, 1, 4).unbind(0)
     ref = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(B * N, 128)
-    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5 if variant != "tc2" else 2e-5)
+
+
+def test_encoder_mha_rejects_unknown_variant(dev, monkeypatch):
+    from rl4co_b200 import native
+
+    monkeypatch.setenv("CO_MHA_VARIANT", "wmma")
+    with pytest.raises(native.NativeLibraryError, match="CO_MHA_VARIANT"):
+        native.encoder_mha(torch.zeros(4, 384, device=dev), 1, 4)
 
 
 def test_sampling_philox_is_valid_and_seeded(dev):
