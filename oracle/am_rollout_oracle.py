@@ -337,13 +337,36 @@ def decoder_forward(weights, env_name, st, cache, num_starts=0, faithful_copies=
 # reference: rl4co/utils/decoding.py
 
 
-def process_logits(logits, mask, temperature=1.0, tanh_clipping=10.0, mask_logits=True):
-    """utils/decoding.py:138-188 (top-k / top-p off)"""
+def keep_top_k(logits, top_k):
+    """utils/decoding.py:109-114: entries below the k-th largest logit of their row become -inf (ties with the
+    k-th value survive)."""
+    kth = torch.topk(logits, top_k).values[..., -1:]
+    return torch.where(logits < kth, torch.full_like(logits, float("-inf")), logits)
+
+
+def keep_top_p(logits, top_p):
+    """utils/decoding.py:117-135: nucleus filter. Rows are sorted ascending, turned into probabilities, and the
+    lower tail whose cumulative mass is <= 1 - top_p is dropped; top_p outside (0, 1) is a no-op."""
+    if not 0.0 < top_p < 1.0:
+        return logits
+    ordered, order = torch.sort(logits, dim=-1)
+    tail = ordered.softmax(dim=-1).cumsum(dim=-1) <= (1.0 - top_p)
+    drop = torch.zeros_like(tail).scatter(-1, order, tail)
+    return torch.where(drop, torch.full_like(logits, float("-inf")), logits)
+
+
+def process_logits(logits, mask, temperature=1.0, tanh_clipping=10.0, mask_logits=True, top_k=0, top_p=0.0):
+    """utils/decoding.py:138-188: tanh clip -> mask -> / temperature -> top-k -> top-p -> log_softmax"""
     if tanh_clipping > 0:
         logits = torch.tanh(logits) * tanh_clipping
     if mask_logits:
         logits[~mask] = float("-inf")
     logits = logits / temperature
+    if top_k > 0:
+        logits = keep_top_k(logits, min(top_k, logits.size(-1)))
+    if top_p > 0:
+        assert top_p <= 1.0, "top-p should be in (0, 1]."
+        logits = keep_top_p(logits, top_p)
     return F.log_softmax(logits, dim=-1)
 
 
@@ -380,7 +403,7 @@ def get_log_likelihood(logprobs):
 
 def rollout(weights, env_name, inst, h, decode_type="greedy", num_starts=None, actions=None,
             noise=None, use_graph_context=True, temperature=1.0, tanh_clipping=10.0,
-            return_trace=False, faithful_copies=True, num_loc=None, generator=None):
+            return_trace=False, faithful_copies=True, num_loc=None, generator=None, top_k=0, top_p=0.0):
     """Decode loop of ConstructivePolicy.forward from encoder output ``h`` on.
 
     decode_type: greedy | sampling | multistart_greedy | multistart_sampling | evaluate
@@ -418,7 +441,7 @@ def rollout(weights, env_name, inst, h, decode_type="greedy", num_starts=None, a
         if return_trace:
             trace["mask"].append(mask.clone())
             trace["logits"].append(logits.clone())
-        logprobs = process_logits(logits, mask, temperature, tanh_clipping)
+        logprobs = process_logits(logits, mask, temperature, tanh_clipping, top_k=top_k, top_p=top_p)
         if decode_type == "evaluate":
             a = actions[..., step]
         elif "greedy" in decode_type:

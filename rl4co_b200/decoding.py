@@ -25,6 +25,22 @@ def get_log_likelihood(logprobs, actions=None, mask=None, return_sum: bool = Tru
     return logprobs.sum(1) if return_sum else logprobs
 
 
+def keep_top_k(logits: torch.Tensor, top_k: int) -> torch.Tensor:
+    """rl4co/utils/decoding.py:109-114 -- logits below the row's k-th largest become -inf (out of place)."""
+    kth = torch.topk(logits, top_k).values[..., -1:]
+    return logits.masked_fill(logits < kth, float("-inf"))
+
+
+def keep_top_p(logits: torch.Tensor, top_p: float) -> torch.Tensor:
+    """rl4co/utils/decoding.py:117-135 -- nucleus filtering with the reference's exact operation order (ascending
+    sort -> softmax -> cumsum -> drop while the cumulative mass is <= 1 - top_p), so the kept sets are identical."""
+    if not 0.0 < top_p < 1.0:
+        return logits
+    ordered, order = torch.sort(logits, dim=-1)
+    tail = ordered.softmax(dim=-1).cumsum(dim=-1) <= (1.0 - top_p)
+    return logits.masked_fill(torch.zeros_like(tail).scatter(-1, order, tail), float("-inf"))
+
+
 class DecodingStrategy:
     """rl4co/utils/decoding.py:191-423"""
 
@@ -36,8 +52,8 @@ class DecodingStrategy:
                  num_starts: int | None = None, multistart: bool = False, select_start_nodes_fn=None,
                  improvement_method_mode: bool = False, select_best: bool = False, store_all_logp: bool = False,
                  **kwargs) -> None:
-        if top_p > 0 or top_k > 0:
-            raise NotImplementedError("top-k / top-p filtering is outside the fused path (SURVEY.md 8f-4)")
+        assert top_p <= 1.0, "top-p should be in (0, 1]."
+        self.top_p, self.top_k = top_p, top_k
         if improvement_method_mode:
             raise NotImplementedError("improvement_method_mode is outside the fused path")
         self.temperature, self.mask_logits, self.tanh_clipping = temperature, mask_logits, tanh_clipping
@@ -99,10 +115,26 @@ class DecodingStrategy:
         """rl4co/utils/decoding.py:344-385, one kernel."""
         assert td is not None, "td must be provided"
         act_io = action.contiguous().clone() if self.select_mode == native.SELECT_EVALUATE else None
+        tanh_clipping, temperature, mask_logits = self.tanh_clipping, self.temperature, self.mask_logits
+        if self.top_k > 0 or self.top_p > 0:
+            # process_logits (decoding.py:168-185) up to the filters with library ops (top-k / sort are not worth
+            # a kernel at N <= 128); the kept set then goes to the selection kernel as its mask, which finishes
+            # with log_softmax over exactly those entries
+            z = torch.tanh(logits) * tanh_clipping if tanh_clipping > 0 else logits
+            if mask_logits:
+                assert mask is not None, "mask must be provided if mask_logits is True"
+                z = z.masked_fill(~mask, float("-inf"))
+            z = z / temperature
+            if self.top_k > 0:
+                z = keep_top_k(z, min(self.top_k, z.size(-1)))
+            if self.top_p > 0:
+                z = keep_top_p(z, self.top_p)
+            logits, mask = z, torch.isfinite(z)
+            tanh_clipping, temperature, mask_logits = 0.0, 1.0, True
         selected, logp, all_lp = native.select_action(
             logits.contiguous(), mask.contiguous() if mask is not None else None, self.select_mode,
-            noise=self._noise(logits), action=act_io, tanh_clipping=self.tanh_clipping, temperature=self.temperature,
-            mask_logits=self.mask_logits, store_all_logp=self.store_all_logp)
+            noise=self._noise(logits), action=act_io, tanh_clipping=tanh_clipping, temperature=temperature,
+            mask_logits=mask_logits, store_all_logp=self.store_all_logp)
         td.set("action", selected)
         self.actions.append(selected)
         self.logprobs.append(all_lp if self.store_all_logp else logp)

@@ -330,6 +330,35 @@ def test_stepping_path_matches_fused_path(golden, dev, name):
     assert torch.equal(ms_f["actions"], ms_s["actions"])
 
 
+@pytest.mark.parametrize("name", ["am_tsp20", "am_cvrp20"])
+@pytest.mark.parametrize("top_k,top_p", [(4, 0.0), (0, 0.8), (6, 0.9)])
+def test_stepping_path_top_k_top_p_sampling_vs_oracle(golden, dev, monkeypatch, name, top_k, top_p):
+    """decoding.py:109-188 with filters on: the stepping path (kernel per stage + library top-k / sort) under the
+    recorded-noise protocol against the free-running oracle; rows may only differ through a genuine near-tie."""
+    from rl4co_b200 import decoding
+
+    g = golden(name)
+    env_name = env_of(name)
+    pol = make_policy(env_name, g.weights(), dev, cache_gemm="cublas")
+    q = g["sampling_noise"]
+    T_max = q.shape[2] if env_name == "tsp" else 2 * (q.shape[2] - 1)
+    qpad = torch.ones(T_max, q.shape[1], q.shape[2])
+    qpad[: q.shape[0]] = q
+    served = iter(qpad.to(dev))
+    monkeypatch.setattr(decoding.Sampling, "_noise", lambda self, logits: next(served).contiguous())
+    out, _, _ = fused_rollout(pol, env_name, g, dev, "sampling", top_k=top_k, top_p=top_p)
+    with torch.inference_mode():
+        ref = O.rollout(g.weights(), env_name, g.inst(), g["h"], decode_type="sampling", top_k=top_k, top_p=top_p,
+                        noise=lambda t, shape: qpad[t], faithful_copies=False)
+    T = min(out["actions"].shape[1], ref["actions"].shape[1])
+    same = _rows_equal(out["actions"].cpu()[:, :T], ref["actions"][:, :T])
+    assert same.float().mean() >= 0.75
+    torch.testing.assert_close(out["log_likelihood"].cpu()[:, :T][same], ref["logprobs"][:, :T][same], rtol=RTOL, atol=ATOL_LP)
+    torch.testing.assert_close(out["reward"].cpu()[same], ref["reward"][same], rtol=RTOL, atol=1e-6)
+    if top_k > 0:  # the filter really bites: no step may have chosen outside the k most likely feasible nodes
+        assert torch.isfinite(out["log_likelihood"]).all()
+
+
 # ------------------------------------------------------------------------------- bigger seeded cases
 @pytest.mark.parametrize("env_name,n,batch", [("tsp", 100, 96), ("cvrp", 100, 96), ("tsp", 50, 128), ("cvrp", 50, 128),
                                               ("tsp", 7, 33), ("cvrp", 5, 33), ("tsp", 128, 16), ("cvrp", 127, 16),

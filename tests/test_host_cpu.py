@@ -220,5 +220,29 @@ def test_unsupported_options_are_rejected():
         FusedAttentionModelDecoder(env_name="op")
     with pytest.raises(NotImplementedError):
         get_decoding_strategy("beam_search")
-    with pytest.raises(NotImplementedError):
-        get_decoding_strategy("sampling", top_k=5)
+    with pytest.raises(AssertionError):
+        get_decoding_strategy("sampling", top_p=1.5)
+
+
+@pytest.mark.parametrize("top_k,top_p", [(3, 0.0), (0, 0.7), (5, 0.9), (40, 0.0), (0, 1.0), (1, 0.5)])
+def test_top_k_top_p_filters_match_oracle(top_k, top_p):
+    """The host-side filters of the stepping path (library ops, device-agnostic) keep exactly the set the oracle's
+    process_logits keeps -- including masked (-inf) entries, ties at the k-th value and a nucleus that ends mid-tie."""
+    from oracle import am_rollout_oracle as O
+    from rl4co_b200.decoding import keep_top_k, keep_top_p
+
+    torch.manual_seed(top_k * 10 + int(top_p * 100))
+    logits = torch.randn(64, 21) * 3
+    logits[:, 5] = logits[:, 4]  # a tie
+    mask = torch.rand(64, 21) > 0.3
+    mask[:, 0] = True
+    z = (torch.tanh(logits) * 10.0).masked_fill(~mask, float("-inf")) / 0.8
+    if top_k > 0:
+        z = keep_top_k(z, min(top_k, z.size(-1)))
+    if top_p > 0:
+        z = keep_top_p(z, top_p)
+    ref = O.process_logits(logits.clone(), mask, temperature=0.8, tanh_clipping=10.0, top_k=top_k, top_p=top_p)
+    assert torch.equal(torch.isfinite(z), torch.isfinite(ref))
+    torch.testing.assert_close(torch.log_softmax(z, -1), ref, rtol=0, atol=0)
+    if top_k > 0 and top_p == 0:
+        assert (torch.isfinite(z).sum(-1) >= torch.minimum(mask.sum(-1), torch.tensor(min(top_k, 21)))).all()

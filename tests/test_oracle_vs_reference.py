@@ -57,6 +57,37 @@ def test_multinomial_is_argmax_p_over_exp_noise(ref, name):
     assert torch.equal(out["actions"], o["actions"])
 
 
+@pytest.mark.parametrize("top_k,top_p", [(3, 0.0), (0, 0.6), (4, 0.8), (50, 0.0), (0, 1.0)])
+def test_top_k_top_p_process_logits_matches_reference(ref, top_k, top_p):
+    """utils/decoding.py:109-188 with the filters on, bit for bit (same torch ops in the same order)."""
+    torch.manual_seed(11 + top_k)
+    logits = torch.randn(32, 20) * 2
+    logits[:, 7] = logits[:, 3]
+    mask = torch.rand(32, 20) > 0.4
+    mask[:, 1] = True
+    want = ref.decoding.process_logits(logits.clone(), mask, temperature=1.3, top_p=top_p, top_k=top_k, tanh_clipping=10.0)
+    got = O.process_logits(logits.clone(), mask, temperature=1.3, tanh_clipping=10.0, top_k=top_k, top_p=top_p)
+    assert torch.equal(want, got)
+
+
+@pytest.mark.parametrize("name", ["tsp", "cvrp"])
+def test_policy_forward_with_filters_matches_reference(ref, name):
+    torch.manual_seed(21)
+    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    env = Env(generator_params=dict(num_loc=20), check_solution=True)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    td0 = env.generator(batch_size=[16])
+    inst = {k: td0[k].clone() for k in td0.keys()}
+    with torch.inference_mode():
+        torch.manual_seed(9)
+        out = pol(env.reset(td0.clone()), env, phase="train", decode_type="sampling", top_k=5, top_p=0.9)
+        torch.manual_seed(9)
+        o = O.policy_forward(W, name, inst, decode_type="sampling", num_layers=1, top_k=5, top_p=0.9)
+    assert torch.equal(out["actions"], o["actions"])
+    torch.testing.assert_close(out["log_likelihood"], o["log_likelihood"], rtol=1e-5, atol=1e-5)
+
+
 def test_generator_matches_reference(ref):
     for name, n in (("tsp", 50), ("cvrp", 50), ("cvrp", 100)):
         Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
