@@ -470,6 +470,74 @@ def rollout(weights, env_name, inst, h, decode_type="greedy", num_starts=None, a
     return out
 
 
+# --------------------------------------------------------------------------- beam search
+# reference: rl4co/utils/decoding.py:464-600 (BeamSearch strategy) inside the loop of constructive/base.py:219-251
+
+
+def rollout_beam_search(weights, env_name, inst, h, beam_width=None, select_best=True, use_graph_context=True,
+                        temperature=1.0, tanh_clipping=10.0, num_loc=None, faithful_copies=True, top_k=0, top_p=0.0):
+    """Beam search over the flat (beam-major: row = w * B + b) expanded batch.
+
+    Every step keeps, per instance, the ``beam_width`` best (parent beam, node) pairs by cumulative log-probability
+    (decoding.py:568-600); the per-step actions / full log-prob rows / parent pointers are recorded in the order
+    they were produced and re-threaded from the last step backwards (decoding.py:529-556); with ``select_best`` the
+    beam with the highest reward per instance is returned (decoding.py:558-566).
+    Returns dict(reward, log_likelihood, actions[*, T], logprobs[*, T]) with * = B (select_best) or B * beam_width."""
+    st = env_reset(env_name, inst)
+    B = st["locs"].shape[0]
+    step_fn = ENV_STEP[env_name]
+    W = beam_width if beam_width is not None else get_num_starts(st["action_mask"].shape[-1], env_name)
+    assert W > 1, "beam width must be larger than 1"
+    nl = num_loc if num_loc is not None else (st["locs"].shape[1] - (1 if env_name == "cvrp" else 0))
+    a0 = select_start_nodes(B, W, nl, env_name, device=st["locs"].device)
+    st = {k: batchify(v, W) for k, v in st.items()}
+    st = step_fn(st, a0)
+    # decoding.py:507-513: the forced first step carries log-prob 0 and parent 0
+    all_lp = [torch.zeros(st["action_mask"].shape, dtype=torch.float32)]
+    acts = [a0]
+    parents = [torch.zeros(B * W, dtype=torch.int32)]
+    cum = torch.zeros(B * W, 1)
+    row_of_instance = torch.arange(B).repeat(W)
+    cache = precompute_cache(weights, h, use_graph_context)
+
+    while not st["done"].all():
+        logits, mask = decoder_forward(weights, env_name, st, cache, W, faithful_copies)
+        lp = process_logits(logits, mask, temperature, tanh_clipping, top_k=top_k, top_p=top_p)
+        N = lp.shape[1]
+        # candidates of instance b side by side: column w * N + n = (parent beam w, node n)
+        cand = torch.cat((lp + cum).split(B), dim=1)
+        best, flat = torch.topk(cand, W, dim=1)
+        cum = torch.cat(best.unbind(1)).unsqueeze(1)
+        flat = torch.cat(flat.unbind(1))
+        a, parent = flat % N, (flat // N).int()
+        src = row_of_instance + parent * B  # the row each surviving beam continues from
+        st = {k: v[src] for k, v in st.items()}
+        assert mask[src].gather(1, a.unsqueeze(-1)).all(), "infeasible action selected"
+        all_lp.append(lp[src])
+        acts.append(a)
+        parents.append(parent)
+        st = step_fn(st, a)
+
+    # backtrack (decoding.py:529-556)
+    A, L = torch.stack(acts, 1), torch.stack(all_lp, 1)
+    seq, seq_lp = [A[:, -1]], [L[:, -1]]
+    cur = parents[-1]
+    for k in reversed(range(len(parents) - 1)):
+        src = row_of_instance + cur * B
+        seq.append(A[src, k])
+        seq_lp.append(L[src, k])
+        cur = parents[k][src]
+    A = torch.stack(seq[::-1], 1)
+    L = torch.stack(seq_lp[::-1], 1)
+    reward = env_reward(env_name, st, A)
+    if select_best:  # decoding.py:558-566
+        idx = unbatchify(reward, W).argmax(dim=1)
+        keep = torch.arange(B) + idx * B
+        A, L, reward = A[keep], L[keep], reward[keep]
+    lp_taken = L.gather(-1, A.unsqueeze(-1)).squeeze(-1)  # get_log_likelihood on 3-D logprobs, decoding.py:48-50
+    return {"reward": reward, "log_likelihood": get_log_likelihood(lp_taken), "actions": A, "logprobs": lp_taken}
+
+
 # --------------------------------------------------------------------------- encoder
 # reference: rl4co/models/zoo/am/encoder.py:68-87, nn/env_embeddings/init.py:55-68,115-136,
 #            nn/graph/attnnet.py:16-106, nn/attention.py:64-134, nn/ops.py:30-54
@@ -519,6 +587,8 @@ def policy_forward(weights, env_name, inst, decode_type="greedy", num_layers=3, 
     """ConstructivePolicy.forward, constructive/base.py:154-263 (encoder + rollout)."""
     st0 = env_reset(env_name, inst)
     h, _ = encoder_forward(weights, env_name, st0, num_layers=num_layers, normalization=normalization)
+    if decode_type == "beam_search":
+        return rollout_beam_search(weights, env_name, inst, h, **kw)
     return rollout(weights, env_name, inst, h, decode_type=decode_type, **kw)
 
 

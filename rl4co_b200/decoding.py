@@ -172,10 +172,99 @@ class Evaluate(DecodingStrategy):
     select_mode = native.SELECT_EVALUATE
 
 
+def beam_expand(logprobs: torch.Tensor, cum: torch.Tensor, beam_width: int):
+    """One beam step (rl4co/utils/decoding.py:568-600) on the flat beam-major batch (row = w * B + b).
+
+    logprobs [B*W, N] full log-prob rows, cum [B*W, 1] cumulative log-prob of each live beam. Per instance the W best
+    (parent beam, node) pairs are kept. Returns (node [B*W], parent [B*W] int32, src_row [B*W], new cum [B*W, 1])."""
+    rows, n = logprobs.shape
+    b = rows // beam_width
+    # the candidates of instance b side by side: column w * N + node
+    cand = (logprobs + cum).view(beam_width, b, n).permute(1, 0, 2).reshape(b, beam_width * n)
+    best, flat = torch.topk(cand, beam_width, dim=1)
+    best, flat = best.t().reshape(-1), flat.t().reshape(-1)  # back to beam-major rows
+    parent = torch.div(flat, n, rounding_mode="floor").int()
+    src = torch.arange(b, device=logprobs.device).repeat(beam_width) + parent * b
+    return flat % n, parent, src, best.unsqueeze(1)
+
+
+def beam_backtrack(actions: torch.Tensor, logprobs: torch.Tensor, parents: torch.Tensor, beam_width: int):
+    """Re-thread the per-step records along the parent pointers, last step first (rl4co/utils/decoding.py:529-556).
+
+    actions [B*W, T], logprobs [B*W, T, N] (or [B*W, T]), parents [B*W, T] int. Row r of the result is the complete
+    sequence that ends in final beam r."""
+    rows, T = actions.shape
+    b = rows // beam_width
+    inst = torch.arange(b, device=actions.device).repeat(beam_width)
+    out_a, out_lp = torch.empty_like(actions), torch.empty_like(logprobs)
+    src = torch.arange(rows, device=actions.device)  # the final beams read their own last record
+    for k in range(T - 1, -1, -1):
+        out_a[:, k], out_lp[:, k] = actions[src, k], logprobs[src, k]
+        if k:
+            src = inst + parents[src, k].long() * b
+    return out_a, out_lp
+
+
+class BeamSearch(DecodingStrategy):
+    """rl4co/utils/decoding.py:464-600. The full log-prob rows come from the selection kernel (`store_all_logp`);
+    the top-W expansion, parent bookkeeping and back-tracking are index arithmetic on the device (library top-k)."""
+
+    name = "beam_search"
+
+    def __init__(self, beam_width=None, select_best=True, **kwargs) -> None:
+        kwargs["store_all_logp"] = True
+        super().__init__(**kwargs)
+        self.beam_width, self.select_best = beam_width, select_best
+        self.cum, self.parents = None, []
+
+    def pre_decoder_hook(self, td: TensorDict, env, action: torch.Tensor | None = None):
+        """decoding.py:490-515: one beam per start node, forced first step with log-prob 0 and parent 0."""
+        if self.beam_width is None:
+            self.beam_width = env.get_num_starts(td)
+        assert self.beam_width > 1, "beam width must be larger than 1"
+        if self.select_start_nodes_fn is not None:
+            action = self.select_start_nodes_fn(td, env, self.beam_width)
+        else:
+            action = env.select_start_nodes(td, num_starts=self.beam_width)
+        td = batchify(td, self.beam_width)
+        td.set("action", action)
+        td = env.step(td)["next"]
+        self.logprobs.append(torch.zeros_like(td["action_mask"], dtype=torch.float32))
+        self.actions.append(action)
+        self.parents.append(torch.zeros_like(action, dtype=torch.int32))
+        self.cum = torch.zeros(action.shape[0], 1, dtype=torch.float32, device=action.device)
+        return td, env, self.beam_width
+
+    def step(self, logits: torch.Tensor, mask: torch.Tensor, td: TensorDict | None = None,
+             action: torch.Tensor | None = None, **kwargs) -> TensorDict:
+        assert td is not None, "td must be provided"
+        self.actions, self.logprobs, kept_a, kept_lp = [], [], self.actions, self.logprobs
+        td = super().step(logits, mask, td)  # one kernel: process_logits -> all log-probs (its arg-max is unused)
+        all_lp = self.logprobs[0]
+        self.actions, self.logprobs = kept_a, kept_lp
+        node, parent, src, self.cum = beam_expand(all_lp, self.cum, self.beam_width)
+        td = td[src]  # every surviving beam continues from its parent's state
+        td.set("action", node)
+        self.actions.append(node)
+        self.logprobs.append(all_lp[src])
+        self.parents.append(parent)
+        return td
+
+    def post_decoder_hook(self, td: TensorDict, env):
+        actions, logprobs = beam_backtrack(torch.stack(self.actions, 1), torch.stack(self.logprobs, 1),
+                                           torch.stack(self.parents, 1), self.beam_width)
+        if self.select_best:  # decoding.py:558-566
+            rewards = env.get_reward(td, actions)
+            b = rewards.shape[0] // self.beam_width
+            keep = torch.arange(b, device=rewards.device) + unbatchify(rewards, self.beam_width).argmax(dim=1) * b
+            return logprobs[keep], actions[keep], td[keep], env
+        return logprobs, actions, td, env
+
+
 def get_decoding_strategy(decoding_strategy, **config) -> DecodingStrategy:
-    """rl4co/utils/decoding.py:17-35 (beam search is outside the fused path)."""
+    """rl4co/utils/decoding.py:17-35 (an unknown name is an error here; the reference falls back to Sampling)."""
     registry = {"greedy": Greedy, "sampling": Sampling, "multistart_greedy": Greedy,
-                "multistart_sampling": Sampling, "evaluate": Evaluate}
+                "multistart_sampling": Sampling, "evaluate": Evaluate, "beam_search": BeamSearch}
     if decoding_strategy not in registry:
         raise NotImplementedError(f"decode type {decoding_strategy!r} is outside the fused path: {list(registry)}")
     if "multistart" in decoding_strategy:

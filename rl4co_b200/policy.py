@@ -78,7 +78,7 @@ class FusedAttentionModelPolicy(nn.Module):
         if not filtered:  # explicit zeros mean "off" (decoding.py:180-185)
             decoding_kwargs.pop("top_k", None), decoding_kwargs.pop("top_p", None)
         use_fused = (decoding_kwargs.pop("fused_rollout", self.fused_rollout) and N <= native.rollout_max_nodes()
-                     and not filtered
+                     and not filtered and decode_type != "beam_search"
                      and not return_entropy and not decoding_kwargs.get("store_all_logp", False)
                      and decoding_kwargs.get("mask_logits", self.mask_logits)
                      and decoding_kwargs.get("select_start_nodes_fn", None) is None)

@@ -219,7 +219,7 @@ def test_unsupported_options_are_rejected():
     with pytest.raises(NotImplementedError):
         FusedAttentionModelDecoder(env_name="op")
     with pytest.raises(NotImplementedError):
-        get_decoding_strategy("beam_search")
+        get_decoding_strategy("lookahead")
     with pytest.raises(AssertionError):
         get_decoding_strategy("sampling", top_p=1.5)
 
@@ -246,3 +246,43 @@ def test_top_k_top_p_filters_match_oracle(top_k, top_p):
     torch.testing.assert_close(torch.log_softmax(z, -1), ref, rtol=0, atol=0)
     if top_k > 0 and top_p == 0:
         assert (torch.isfinite(z).sum(-1) >= torch.minimum(mask.sum(-1), torch.tensor(min(top_k, 21)))).all()
+
+
+@pytest.mark.parametrize("B,W,N", [(5, 3, 7), (1, 4, 4), (6, 2, 11)])
+def test_beam_expand_and_backtrack(B, W, N):
+    """Beam bookkeeping of the stepping path (device-agnostic index arithmetic): the expansion keeps the W best
+    (parent, node) pairs per instance in the reference's row order, and back-tracking returns, for every final beam,
+    the sequence obtained by following its parent pointers one step at a time."""
+    from rl4co_b200.decoding import beam_backtrack, beam_expand
+
+    torch.manual_seed(B * 100 + W * 10 + N)
+    T = 6
+    cum = torch.zeros(B * W, 1)
+    acts, lps, pars = [torch.randint(0, N, (B * W,))], [torch.zeros(B * W, N)], [torch.zeros(B * W, dtype=torch.int32)]
+    for _ in range(T - 1):
+        lp = torch.log_softmax(torch.randn(B * W, N) * 2, -1)
+        lp[torch.rand(B * W, N) < 0.2] = float("-inf")
+        lp[:, 0] = torch.where(torch.isinf(lp).all(1), torch.zeros(()), lp[:, 0])
+        node, parent, src, new_cum = beam_expand(lp, cum, W)
+        # per-instance brute force: all (w, n) pairs ranked by cumulative log-prob
+        for b in range(B):
+            pairs = sorted(((float(lp[w * B + b, n] + cum[w * B + b, 0]), w, n) for w in range(W) for n in range(N)),
+                           key=lambda x: -x[0])[:W]
+            for k, (score, w, n) in enumerate(pairs):
+                r = k * B + b
+                assert abs(float(new_cum[r, 0]) - score) < 1e-6
+                if sum(abs(p[0] - score) < 1e-9 for p in pairs) == 1:  # untied: the exact pair must match
+                    assert (int(parent[r]), int(node[r]), int(src[r])) == (w, n, w * B + b)
+        cum = new_cum
+        acts.append(node), lps.append(lp[src]), pars.append(parent)
+    A, L, P = torch.stack(acts, 1), torch.stack(lps, 1), torch.stack(pars, 1)
+    out_a, out_lp = beam_backtrack(A, L, P, W)
+    for r in range(B * W):
+        cur, b = r, r % B
+        for k in range(T - 1, -1, -1):
+            assert out_a[r, k] == A[cur, k]
+            assert torch.equal(out_lp[r, k], L[cur, k])
+            cur = b + int(P[cur, k]) * B
+    # a sequence's cumulative log-prob equals the beam score it ended with
+    got = out_lp.gather(-1, out_a.unsqueeze(-1)).squeeze(-1).sum(1)
+    torch.testing.assert_close(got, cum.squeeze(1), rtol=1e-5, atol=1e-5)

@@ -88,6 +88,26 @@ def test_policy_forward_with_filters_matches_reference(ref, name):
     torch.testing.assert_close(out["log_likelihood"], o["log_likelihood"], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("name,n", [("tsp", 12), ("cvrp", 11)])
+@pytest.mark.parametrize("beam_width,select_best", [(3, True), (4, False), (None, True)])
+def test_beam_search_matches_reference(ref, name, n, beam_width, select_best):
+    """utils/decoding.py:464-600 through the live ConstructivePolicy loop."""
+    torch.manual_seed(300 + n)
+    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    env = Env(generator_params=dict(num_loc=n), check_solution=True)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    td0 = env.generator(batch_size=[5])
+    inst = {k: td0[k].clone() for k in td0.keys()}
+    kw = {} if beam_width is None else {"beam_width": beam_width}
+    with torch.inference_mode():
+        out = pol(env.reset(td0.clone()), env, phase="test", decode_type="beam_search", select_best=select_best, **kw)
+        o = O.policy_forward(W, name, inst, decode_type="beam_search", num_layers=1, select_best=select_best, **kw)
+    assert torch.equal(out["actions"], o["actions"])
+    torch.testing.assert_close(out["reward"], o["reward"], rtol=1e-6, atol=0)
+    torch.testing.assert_close(out["log_likelihood"], o["log_likelihood"], rtol=1e-5, atol=1e-5)
+
+
 def test_generator_matches_reference(ref):
     for name, n in (("tsp", 50), ("cvrp", 50), ("cvrp", 100)):
         Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
