@@ -161,7 +161,7 @@ def cpu_reference_run(env_name, num_loc, batch, decode_type, steps, warmup):
     probe = O.generate_instances(env_name, min(256, batch), num_loc)
     best = (None, float("inf"))
     with torch.inference_mode():
-        for nt in sorted({min(c, cores) for c in (8, 16, 32, 64, cores)}):
+        for nt in sorted({min(c, cores) for c in (8, 16, 32, 64)}):  # the full width of a 100+-core host is far slower
             torch.set_num_threads(nt)
             st0 = O.env_reset(env_name, probe)
             h, _ = O.encoder_forward(W, env_name, st0, num_layers=3)
@@ -199,7 +199,7 @@ def run_reference(args):
     r = cpu_reference_run(args.env, args.num_loc, args.cpu_batch, args.decode_type, args.steps, min(args.warmup, 1))
     val = r["selections"] / r["policy_forward_s"]
     sample = (f"{args.env.upper()}-{args.num_loc} {args.decode_type} policy-forward (encoder+decode+reward), "
-              f"B={args.cpu_batch} per step, torch CPU fp32, {r['threads']} threads (best of 8/16/32/64/all on a {r['host_cores']}-core host)")
+              f"B={args.cpu_batch} per step, torch CPU fp32, {r['threads']} threads (best of 8/16/32/64 on a {r['host_cores']}-core host)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": r["policy_forward_s"] * 1e3, "higher_is_better": True,
@@ -367,7 +367,7 @@ def run_ours(args):
         cpu_baseline = {
             "value": r["selections"] / r["policy_forward_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
             "sample": f"{env_name.upper()}-{n} {args.decode_type} policy-forward, B={args.cpu_batch}, torch CPU fp32, "
-                      f"{r['threads']} threads (best of 8/16/32/64/all on a {r['host_cores']}-core host), mean of 2 after 1 warm-up",
+                      f"{r['threads']} threads (best of 8/16/32/64 on a {r['host_cores']}-core host), mean of 2 after 1 warm-up",
             "decode_only_value": r["selections"] / r["decode_only_s"]}
 
     line = {
