@@ -281,14 +281,20 @@ def run_ours(args):
             baseline_allreduce(res["reward"])
         return res
 
+    host_out = {}  # pinned result buffers, reused across steps (a pageable destination is copied through a bounce buffer)
+
     def e2e_step():
         with torch.inference_mode():
             td = TensorDict({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}, batch_size=[B])
             td = env.reset(td)
             out = policy(td, env, phase="test", decode_type=args.decode_type)
             baseline_allreduce(out["reward"])
-            host = {k: out[k].to("cpu", non_blocking=False) for k in ("actions", "reward", "log_likelihood")}
-        return host
+            for k in ("actions", "reward", "log_likelihood"):
+                if k not in host_out or host_out[k].shape != out[k].shape:
+                    host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+                host_out[k].copy_(out[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the results are on the host when the step returns
+        return host_out
 
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
