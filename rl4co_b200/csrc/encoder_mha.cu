@@ -147,7 +147,8 @@ static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t s
 }
 
 int launch_encoder_mha_tc(const float* qkv, float* out, int B, int N, cudaStream_t stream);   // encoder_mha_tc.cu
-int launch_encoder_mha_tc2(const float* qkv, float* out, int B, int N, cudaStream_t stream);               // encoder_mha_tc2.cu
+int launch_encoder_mha_tc2(const float* qkv, float* out, int B, int N, cudaStream_t stream);  // encoder_mha_tc2.cu
+int launch_encoder_mha_tc3(const float* qkv, float* out, int B, int N, cudaStream_t stream);  // encoder_mha_tc3.cu (draft)
 
 }  // namespace co
 
@@ -164,6 +165,7 @@ extern "C" int co_encoder_mha(const float* qkv, float* out, int B, int N, void* 
   // scores for N > 64, all-SIMT below (a 128 x 128 score tile is mostly padding there).
   const char* ev = getenv("CO_MHA_VARIANT");
   if (ev && !strcmp(ev, "tc2")) return launch_encoder_mha_tc2(qkv, out, B, N, st);
+  if (ev && !strcmp(ev, "tc3-unverified")) return launch_encoder_mha_tc3(qkv, out, B, N, st);  // draft, never run yet
   if (ev ? !strcmp(ev, "tc") : N > 64) return launch_encoder_mha_tc(qkv, out, B, N, st);
   if (ev && strcmp(ev, "simt")) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: CO_MHA_VARIANT must be simt, tc or tc2%s");
   if (N <= 32) return launch_mha<1, 1>(qkv, out, B, N, st);

@@ -1,4 +1,5 @@
-"""Time + check co_encoder_mha variants against torch SDPA (fp64 reference). Usage: B=65536 python tools/bench_mha.py"""
+"""Time + check co_encoder_mha variants against torch SDPA (fp64 reference).
+Usage: B=65536 NS=100 VARIANTS=simt,tc,tc2 python tools/bench_mha.py   (the never-run draft: VARIANTS=tc3-unverified, small B, under `timeout`)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
