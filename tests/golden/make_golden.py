@@ -146,6 +146,37 @@ def am_fixture(name, n, batch, seed, ms_batch=3):
     return out
 
 
+def decoding_fixture(name, n, batch, seed):
+    """Beam search and top-k / top-p sampling (utils/decoding.py:109-188,464-600) on the SAME policy and instances
+    as am_fixture(name, n, batch, seed): the seed sequence up to the generator call is replayed, weights and
+    instances are not stored again (`h` is, as a guard)."""
+    torch.manual_seed(seed)
+    env = make_env(name, n)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    td0 = env.generator(batch_size=[batch])
+    out = {}
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        h, _ = pol.encoder(td)
+        out["h"] = npy(h)
+        for tag, kw in (("beam3_best", dict(beam_width=3, select_best=True)),
+                        ("beam4_all", dict(beam_width=4, select_best=False)),
+                        ("beamN_best", dict(select_best=True))):
+            o = pol(td.clone(), env, phase="test", decode_type="beam_search", return_sum_log_likelihood=False, **kw)
+            out.update({f"{tag}_actions": npy(o["actions"]), f"{tag}_logprobs": npy(o["log_likelihood"]),
+                        f"{tag}_reward": npy(o["reward"])})
+        for i, (tag, kw) in enumerate((("topk4", dict(top_k=4)), ("topp80", dict(top_p=0.8)),
+                                       ("topk6_topp90", dict(top_k=6, top_p=0.9)))):
+            torch.manual_seed(seed + 10 + i)
+            o = pol(td.clone(), env, phase="train", decode_type="sampling", return_sum_log_likelihood=False, **kw)
+            T = o["actions"].shape[1]
+            torch.manual_seed(seed + 10 + i)  # the Exp(1) draws torch.multinomial consumed, one [B, N] block per step
+            q = torch.stack([torch.empty(batch, td["action_mask"].shape[-1]).exponential_(1) for _ in range(T)])
+            out.update({f"{tag}_actions": npy(o["actions"]), f"{tag}_logprobs": npy(o["log_likelihood"]),
+                        f"{tag}_reward": npy(o["reward"]), f"{tag}_noise": npy(q)})
+    return out
+
+
 def encoder_fixture(name, n, batch, seed, normalization):
     torch.manual_seed(seed)
     env = make_env(name, n)
@@ -199,8 +230,13 @@ def main():
         "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
         "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
         "layout": layout_fixture,
+        "dec_tsp20": lambda: decoding_fixture("tsp", 20, 8, 200),
+        "dec_cvrp20": lambda: decoding_fixture("cvrp", 20, 8, 201),
     }
+    only = set(sys.argv[1:])  # `python make_golden.py dec_tsp20 dec_cvrp20` regenerates just those files
     for name, fn in jobs.items():
+        if only and name not in only:
+            continue
         data = fn()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **data)

@@ -66,6 +66,34 @@ def test_am_teacher_forced(golden, name):
     torch.testing.assert_close(out["reward"], g["eval_reward"], rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("name", ["tsp20", "cvrp20"])
+@pytest.mark.parametrize("tag,kw", [("beam3_best", dict(beam_width=3, select_best=True)),
+                                    ("beam4_all", dict(beam_width=4, select_best=False)),
+                                    ("beamN_best", dict(select_best=True))])
+def test_am_beam_search(golden, name, tag, kw):
+    """utils/decoding.py:464-600 as recorded from the reference (tests/golden/dec_*.npz; same policy and instances
+    as am_*.npz -- the stored encoder output guards that)."""
+    g, d = golden("am_" + name), golden("dec_" + name)
+    assert torch.equal(g["h"], d["h"])
+    out = O.rollout_beam_search(g.weights(), env_of(name), g.inst(), g["h"], **kw)
+    assert torch.equal(out["actions"], d[tag + "_actions"])
+    torch.testing.assert_close(out["logprobs"], d[tag + "_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], d[tag + "_reward"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["tsp20", "cvrp20"])
+@pytest.mark.parametrize("tag,kw", [("topk4", dict(top_k=4)), ("topp80", dict(top_p=0.8)),
+                                    ("topk6_topp90", dict(top_k=6, top_p=0.9))])
+def test_am_top_k_top_p_sampling_with_recorded_noise(golden, name, tag, kw):
+    """utils/decoding.py:109-188 with the filters on, under the recorded-noise protocol."""
+    g, d = golden("am_" + name), golden("dec_" + name)
+    q = d[tag + "_noise"]
+    out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], "sampling", noise=lambda t, shape: q[t], **kw)
+    assert torch.equal(out["actions"], d[tag + "_actions"])
+    torch.testing.assert_close(out["logprobs"], d[tag + "_logprobs"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["reward"], d[tag + "_reward"], rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("name", AM_FIX)
 def test_am_multistart_and_pomo(golden, name):
     g = golden(name)
