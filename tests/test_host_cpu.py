@@ -286,3 +286,24 @@ def test_beam_expand_and_backtrack(B, W, N):
     # a sequence's cumulative log-prob equals the beam score it ended with
     got = out_lp.gather(-1, out_a.unsqueeze(-1)).squeeze(-1).sum(1)
     torch.testing.assert_close(got, cum.squeeze(1), rtol=1e-5, atol=1e-5)
+
+
+def test_bench_reference_arm_line_schema():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU and prints one JSON
+    line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-batch", "8", "--num-loc", "20"], capture_output=True, text=True,
+                         timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["unit"] == "selections/s"
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
