@@ -27,8 +27,11 @@ rl4co cannot be imported as-is in this image: ``tensordict``, ``torchrl``,
 Nothing here restates reference arithmetic: every number produced through this
 module is computed by reference code + PyTorch.
 
-``/root/reference`` does not exist on the GPU box, so this module is only usable
-in the build container; tests that need it skip when it is missing.
+``/root/reference`` does not exist on the GPU box.  ``oracle/make_ref.py`` (called by
+``__graft_entry__.build()`` in the build container) stages the same unmodified files under the
+git-ignored ``oracle/_ref/``, which travels with the snapshot; this module uses
+``/root/reference`` when present and ``oracle/_ref`` otherwise.  Tests that need it skip when
+neither exists.
 """
 
 from __future__ import annotations
@@ -38,11 +41,28 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RL4CO_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("RL4CO_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/rl4co"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "rl4co"))
+
+
+def reference_kind() -> str:
+    """'reference' = live tree, 'staged' = oracle/_ref copy (same bytes, see MANIFEST.json)."""
+    return "staged" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED) else "reference"
 
 
 def _mod(name: str, **attrs) -> types.ModuleType:
@@ -157,6 +177,8 @@ def install() -> None:
     _pkg("rl4co.envs.routing", "rl4co/envs/routing")
     _pkg("rl4co.envs.routing.tsp", "rl4co/envs/routing/tsp")
     _pkg("rl4co.envs.routing.cvrp", "rl4co/envs/routing/cvrp")
+    _pkg("rl4co.envs.routing.sdvrp", "rl4co/envs/routing/sdvrp")
+    _pkg("rl4co.envs.routing.op", "rl4co/envs/routing/op")
     _pkg("rl4co.models", "rl4co/models")
     _pkg("rl4co.models.common", "rl4co/models/common")
     _pkg("rl4co.models.nn", "rl4co/models/nn")
@@ -164,6 +186,9 @@ def install() -> None:
     _pkg("rl4co.models.nn.env_embeddings", "rl4co/models/nn/env_embeddings")
     _pkg("rl4co.models.zoo", "rl4co/models/zoo")
     _pkg("rl4co.models.zoo.am", "rl4co/models/zoo/am")
+    _pkg("rl4co.models.rl", "rl4co/models/rl")
+    _pkg("rl4co.models.rl.common", "rl4co/models/rl/common")
+    _pkg("rl4co.models.rl.reinforce", "rl4co/models/rl/reinforce")
 
     base = importlib.import_module("rl4co.envs.common.base")
     envs = sys.modules["rl4co.envs"]

@@ -148,7 +148,7 @@ static int launch_mha(const float* qkv, float* out, int B, int N, cudaStream_t s
 
 int launch_encoder_mha_tc(const float* qkv, float* out, int B, int N, cudaStream_t stream);   // encoder_mha_tc.cu
 int launch_encoder_mha_tc2(const float* qkv, float* out, int B, int N, cudaStream_t stream);  // encoder_mha_tc2.cu
-int launch_encoder_mha_tc3(const float* qkv, float* out, int B, int N, cudaStream_t stream);  // encoder_mha_tc3.cu (draft)
+int launch_encoder_mha_tc3(const float* qkv, float* out, int B, int N, cudaStream_t stream);  // encoder_mha_tc3.cu
 
 }  // namespace co
 
@@ -161,13 +161,14 @@ extern "C" int co_encoder_mha(const float* qkv, float* out, int B, int N, void* 
   if (((uintptr_t)qkv | (uintptr_t)out) & 15) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: pointers must be 16-byte aligned%s");
   if (B == 0) return CO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // CO_MHA_VARIANT = simt | tc | tc2 forces one kernel (read per call so tests can switch); default: tensor-core
-  // scores for N > 64, all-SIMT below (a 128 x 128 score tile is mostly padding there).
+  // CO_MHA_VARIANT = simt | tc | tc2 | tc3 forces one kernel (read per call so tests can switch); default: tc3
+  // (scores AND P.V on the tensor core, P through TMEM) for N > 64, all-SIMT below (a 128 x 128 score tile is mostly
+  // padding there).
   const char* ev = getenv("CO_MHA_VARIANT");
   if (ev && !strcmp(ev, "tc2")) return launch_encoder_mha_tc2(qkv, out, B, N, st);
-  if (ev && !strcmp(ev, "tc3-unverified")) return launch_encoder_mha_tc3(qkv, out, B, N, st);  // draft, never run yet
-  if (ev ? !strcmp(ev, "tc") : N > 64) return launch_encoder_mha_tc(qkv, out, B, N, st);
-  if (ev && strcmp(ev, "simt")) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: CO_MHA_VARIANT must be simt, tc or tc2%s");
+  if (ev && !strcmp(ev, "tc")) return launch_encoder_mha_tc(qkv, out, B, N, st);
+  if (ev ? !strcmp(ev, "tc3") : N > 64) return launch_encoder_mha_tc3(qkv, out, B, N, st);
+  if (ev && strcmp(ev, "simt")) return fail(CO_ERR_BAD_ARG, "co_encoder_mha: CO_MHA_VARIANT must be simt, tc, tc2 or tc3%s");
   if (N <= 32) return launch_mha<1, 1>(qkv, out, B, N, st);
   if (N <= 64) return launch_mha<2, 1>(qkv, out, B, N, st);
   return launch_mha<4, 1>(qkv, out, B, N, st);

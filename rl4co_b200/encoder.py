@@ -8,8 +8,12 @@ with the reference's module tree so that a reference ``state_dict`` loads unchan
   Normalization           rl4co/models/nn/ops.py:30-54
   MLP                     rl4co/models/nn/mlp.py:8-60
 
-It runs once per instance (dense [B*N,128] GEMMs + NxN attention through cuBLAS / SDPA); the
-per-node-selection loop it feeds is the hand-written part of this package.
+It runs once per instance.  Inference (no autograd, eval mode, CUDA): every nn.Linear runs on the
+hand-written tcgen05 3xTF32 GEMM (`co_gemm_tf32x3`; bias / ReLU / skip connection / eval-mode
+BatchNorm folded into its epilogue) and the attention core on `co_encoder_mha` (tcgen05 scores
+and P.V for N > 64) -- `_net_fused` below.  Still stock torch ops there: the K = 2 / 3 init
+embedding, the graph-context mean + Linear of the decoder, and instance normalisation.  Under
+autograd (training) the stock modules (cuBLAS / SDPA) run, because the kernels are forward-only.
 """
 
 from __future__ import annotations

@@ -238,7 +238,14 @@ class FusedCVRPEnv(FusedEnvBase):
             },
             batch_size=batch_size,
         )
-        td_reset.set("action_mask", self.get_action_mask(td_reset))
+        if td_reset["visited"].is_cuda:
+            mask = self.get_action_mask(td_reset)
+        else:
+            # reset only allocates state and works on any device (module docstring): the initial mask of
+            # cvrp/env.py:126-136 with nothing visited and the vehicle at the depot, in torch
+            fits = ~(td_reset["demand"] + td_reset["used_capacity"] > td_reset["vehicle_capacity"] + 1e-5)
+            mask = torch.cat((~fits.any(-1, keepdim=True), fits), -1)
+        td_reset.set("action_mask", mask)
         return td_reset
 
     def _step(self, td: TensorDict) -> TensorDict:
@@ -298,6 +305,24 @@ class FusedCVRPEnv(FusedEnvBase):
 
 
 ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv}
+
+
+def _register_with_torchrl() -> bool:
+    """When torchrl is importable, make the fused envs (virtual) subclasses of `torchrl.envs.EnvBase`, so
+    `isinstance(env, EnvBase)` checks in user code hold.  Virtual (`ABCMeta.register`) on purpose: reset / step
+    bookkeeping stays the few lines above instead of torchrl's spec machinery (rl4co's loops only use
+    reset / step / get_reward)."""
+    try:
+        from torchrl.envs import EnvBase
+    except Exception:
+        return False
+    if hasattr(EnvBase, "register"):
+        EnvBase.register(FusedEnvBase)
+        return True
+    return False
+
+
+_register_with_torchrl()
 
 
 def get_env(env_name: str, *args, **kwargs) -> FusedEnvBase:

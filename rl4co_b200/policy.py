@@ -77,7 +77,13 @@ class FusedAttentionModelPolicy(nn.Module):
         filtered = decoding_kwargs.get("top_k", 0) > 0 or decoding_kwargs.get("top_p", 0.0) > 0
         if not filtered:  # explicit zeros mean "off" (decoding.py:180-185)
             decoding_kwargs.pop("top_k", None), decoding_kwargs.pop("top_p", None)
+        # the kernels' fixed-offset log-softmax needs a tanh clip and 2*clip/T within exp's fp32 range
+        # (exp(-2*clip/T) must not flush to zero): other settings take the stepping path
+        clip_ = decoding_kwargs.get("tanh_clipping", self.tanh_clipping)
+        temp_ = decoding_kwargs.get("temperature", self.temperature)
+        softmax_ok = clip_ > 0 and temp_ > 0 and 2.0 * clip_ / temp_ < 80.0
         use_fused = (decoding_kwargs.pop("fused_rollout", self.fused_rollout) and N <= native.rollout_max_nodes()
+                     and softmax_ok
                      and not filtered and decode_type != "beam_search"
                      and not return_entropy and not decoding_kwargs.get("store_all_logp", False)
                      and decoding_kwargs.get("mask_logits", self.mask_logits)
@@ -109,6 +115,7 @@ class FusedAttentionModelPolicy(nn.Module):
         sampling_noise = kw.pop("sampling_noise", "philox")  # "philox" (in-kernel) | "torch" (generator)
         seed = kw.pop("seed", None)
         kw.pop("multistart", None)
+        philox_offset = kw.pop("philox_offset", None)
         if kw:
             raise NotImplementedError(f"decoding kwargs outside the fused path: {list(kw)}")
 
@@ -139,6 +146,11 @@ class FusedAttentionModelPolicy(nn.Module):
             mode = native.SELECT_SAMPLE_NOISE if noise is not None else native.SELECT_SAMPLE_PHILOX
             if seed is None and mode == native.SELECT_SAMPLE_PHILOX:
                 seed = int(torch.randint(0, 2**62, (1,)).item())
+            if mode == native.SELECT_SAMPLE_PHILOX and philox_offset is None:
+                # identically seeded ranks must not draw identical streams
+                from .distributed import rank_stream_offset
+
+                philox_offset = rank_stream_offset()
         else:
             raise NotImplementedError(f"decode type {decode_type!r} is outside the fused path")
 
@@ -151,7 +163,7 @@ class FusedAttentionModelPolicy(nn.Module):
                 cached.q_placeholder, cached.w_capacity, td["locs"].contiguous(), demand, vcap, B, N, num_starts=S,
                 forced_start=forced_start, num_loc=num_loc, T_max=T_max, forced_actions=forced,
                 noise=noise.contiguous() if noise is not None else None, tanh_clipping=tanh_clipping,
-                temperature=temperature, seed=seed or 0)
+                temperature=temperature, seed=seed or 0, offset=philox_offset or 0)
         if env_name == "tsp":
             T = N
         elif decode_type == "evaluate":
@@ -161,6 +173,16 @@ class FusedAttentionModelPolicy(nn.Module):
         out_actions = res["actions"][:, :T]
         logprobs = res["logprobs"][:, :T]
         reward = res["reward"]
+        if torch.is_grad_enabled() and hidden.requires_grad:
+            # the whole-episode kernel is forward-only: under autograd (e.g. the reference's
+            # REINFORCE.shared_step calling policy(td, env, phase="train") and then loss.backward(),
+            # reinforce.py:59-69) the log-probs of exactly the selected actions are recomputed by the
+            # differentiable teacher-forced pass, so `log_likelihood` carries a grad_fn
+            from .reinforce import evaluate_log_likelihood
+
+            logprobs = evaluate_log_likelihood(self, td, env, out_actions.contiguous(), hidden=hidden,
+                                               return_sum=False, temperature=temperature, tanh_clipping=tanh_clipping,
+                                               forced_first=forced_start)
         if calc_reward and env.check_solution:
             td_chk = td if S == 1 else TensorDict({k: td[k] for k in ("locs", "demand", "vehicle_capacity") if k in td.keys()},
                                                   batch_size=td.batch_size)

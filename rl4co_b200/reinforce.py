@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from . import native
-from .distributed import global_mean_baseline
+from .distributed import global_mean_baseline, sync_gradients
 from .ops import StateAugmentation, batchify, gather_by_index, unbatchify
 from .tensordict import TensorDict
 
@@ -36,8 +36,11 @@ def replay_states(env_name: str, td: TensorDict, actions: torch.Tensor):
     B, T = actions.shape
     N = td["locs"].shape[-2]
     dev = actions.device
-    onehot = F.one_hot(actions, N)                                  # [B,T,N]
-    visited_before = (onehot.cumsum(1) - onehot) > 0               # visited strictly before step t
+    # visited strictly before step t, as bool: scatter a one-hot and take a running max along T (an int64
+    # F.one_hot + int64 cumsum is 16 bytes per (trajectory, step, node): 8 GB for POMO TSP-100 at B = 512)
+    onehot = torch.zeros(B, T, N, dtype=torch.uint8, device=dev).scatter_(2, actions.unsqueeze(-1), 1)
+    visited_before = torch.cat([torch.zeros(B, 1, N, dtype=torch.uint8, device=dev),
+                                onehot[:, :-1].cummax(1)[0]], 1).bool()
     prev = torch.cat([torch.zeros(B, 1, dtype=actions.dtype, device=dev), actions[:, :-1]], 1)
     if env_name == "tsp":
         mask = ~visited_before
@@ -61,7 +64,8 @@ def replay_states(env_name: str, td: TensorDict, actions: torch.Tensor):
 
 
 def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, hidden=None,
-                            return_sum: bool = True) -> torch.Tensor:
+                            return_sum: bool = True, temperature=None, tanh_clipping=None,
+                            forced_first=None) -> torch.Tensor:
     """log pi(actions | instance) with autograd, equal (<= fp32 round-off) to what the rollout
     kernel reported for the same actions.  `td` is the reset state (multistart: the [B] state,
     actions [S*B, T] in the reference's start-major order)."""
@@ -87,7 +91,8 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     mask = mask.view(B, Q, N)
     prev_q = prev.reshape(B, Q)
     wc = dec.context_embedding.project_context.weight
-    forced_first = S > 1  # multistart: step 0 is the forced start node with log-prob 0
+    if forced_first is None:
+        forced_first = S > 1  # multistart: step 0 is the forced start node with log-prob 0
     if env_name == "tsp":
         ctx = torch.cat([gather_by_index(hidden, first.reshape(B, Q)), gather_by_index(hidden, prev_q)], -1)  # [B,Q,2E]
         q = F.linear(ctx, wc)
@@ -109,10 +114,10 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     o = o.transpose(1, 2).reshape(B, Q, E)
     glimpse = dec.pointer.project_out(o)
     logits = torch.bmm(glimpse, L.transpose(1, 2)) / math.sqrt(E)
-    clip = policy.tanh_clipping
+    clip = policy.tanh_clipping if tanh_clipping is None else tanh_clipping
     if clip > 0:
         logits = torch.tanh(logits) * clip
-    logits = logits.masked_fill(~mask, float("-inf")) / policy.temperature
+    logits = logits.masked_fill(~mask, float("-inf")) / (policy.temperature if temperature is None else temperature)
     logp = F.log_softmax(logits, -1).gather(-1, acts.reshape(B, Q)[..., None]).squeeze(-1).view(B * S, T)
     if forced_first:
         logp = torch.cat([torch.zeros_like(logp[:, :1]), logp[:, 1:]], 1)
@@ -213,6 +218,7 @@ def reinforce_step(policy, env, td, baseline, optimizer=None, decode_type="sampl
     if optimizer is not None:
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
+        sync_gradients(policy.parameters())  # DDP-equivalent gradient averaging (no-op on one rank)
         if max_grad_norm:
             torch.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)
         optimizer.step()
@@ -241,6 +247,7 @@ def pomo_step(policy, env, td, num_augment=8, num_starts=None, phase="test", opt
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
+            sync_gradients(policy.parameters())
             optimizer.step()
         return {"loss": loss.detach(), "reward": reward, "max_reward": reward.max(-1)[0]}
     with torch.inference_mode():

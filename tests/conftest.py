@@ -63,3 +63,29 @@ def golden():
 
 def env_of(name):
     return "tsp" if "tsp" in name else "cvrp"
+
+
+def name_seeded_weights(state_dict, seed):
+    """Mirror of tests/golden/make_golden.py::name_seeded_weights: weights that depend only on
+    (parameter name, shape, seed), so a fixture need not store them."""
+    import zlib
+
+    new = {}
+    for k in sorted(state_dict.keys()):
+        v = state_dict[k]
+        if not v.dtype.is_floating_point:
+            new[k] = v.clone()
+            continue
+        gen = torch.Generator().manual_seed(seed * 1_000_003 + zlib.crc32(k.encode()))
+        u = torch.rand(v.shape, generator=gen) * 2 - 1
+        if v.dim() >= 2:
+            new[k] = u / (v.shape[-1] ** 0.5)
+        elif "W_placeholder" in k:
+            new[k] = u
+        elif "norm" in k and k.endswith("weight"):
+            new[k] = 1 + 0.1 * u
+        elif k.endswith("running_var"):
+            new[k] = 1 + 0.25 * u
+        else:
+            new[k] = 0.1 * u
+    return new

@@ -88,7 +88,9 @@ class Recorder:
         return npy(lg), npy(mk)
 
 
-def am_fixture(name, n, batch, seed, ms_batch=3):
+def am_fixture(name, n, batch, seed, ms_batch=3, lean=False):
+    """`lean` drops the recorded sampling / multistart logits (4 MB at N = 100); the greedy and
+    teacher-forced logits, every action / log-prob / reward and the consumed noise stay."""
     torch.manual_seed(seed)
     env = make_env(name, n)
     pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
@@ -118,7 +120,9 @@ def am_fixture(name, n, batch, seed, ms_batch=3):
         torch.manual_seed(seed + 1)
         q = torch.stack([torch.empty(batch, lg.shape[-1]).exponential_(1) for _ in range(T)])
         out.update(sampling_actions=npy(o["actions"]), sampling_logprobs=npy(o["log_likelihood"]),
-                   sampling_reward=npy(o["reward"]), sampling_noise=npy(q), sampling_logits=lg)
+                   sampling_reward=npy(o["reward"]), sampling_noise=npy(q))
+        if not lean:
+            out.update(sampling_logits=lg)
         # -- teacher-forced evaluation of an independent (random-policy) action sequence
         torch.manual_seed(seed + 2)
         tdr = env.reset(td0.clone())
@@ -137,7 +141,9 @@ def am_fixture(name, n, batch, seed, ms_batch=3):
         o = pol(tdm.clone(), env, phase="test", decode_type="multistart_greedy", return_sum_log_likelihood=False)
         lg, mk = rec.pop()
         out.update(ms_actions=npy(o["actions"]), ms_logprobs=npy(o["log_likelihood"]), ms_reward=npy(o["reward"]),
-                   ms_logits=lg, ms_batch=np.int64(ms_batch))
+                   ms_batch=np.int64(ms_batch))
+        if not lean:
+            out.update(ms_logits=lg)
         # -- POMO-style: no graph context (pomo/model.py:59-63)
         polp = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1, use_graph_context=False).eval()
         polp.load_state_dict(pol.state_dict())
@@ -198,6 +204,67 @@ def encoder_fixture(name, n, batch, seed, normalization):
     return out
 
 
+def name_seeded_weights(module, seed):
+    """Deterministic weights that depend only on (parameter name, shape, seed) -- not on module
+    construction order -- so the consumer regenerates them instead of the fixture storing 5 MB:
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for matrices (torch.nn.Linear's range), U(-.1,.1) for
+    vectors, norm weights 1 + U(-.1,.1).  Mirrored by tests/conftest.py::name_seeded_weights."""
+    import zlib
+
+    sd = module.state_dict()
+    new = {}
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        if not v.dtype.is_floating_point:
+            new[k] = v.clone()
+            continue
+        gen = torch.Generator().manual_seed(seed * 1_000_003 + zlib.crc32(k.encode()))
+        u = torch.rand(v.shape, generator=gen) * 2 - 1
+        if v.dim() >= 2:
+            new[k] = u / (v.shape[-1] ** 0.5)
+        elif "W_placeholder" in k:
+            new[k] = u
+        elif "norm" in k and k.endswith("weight"):
+            new[k] = 1 + 0.1 * u
+        elif k.endswith("running_var"):
+            new[k] = 1 + 0.25 * u
+        else:
+            new[k] = 0.1 * u
+    module.load_state_dict(new)
+    return new
+
+
+def pomo_fixture(n, batch, seed, num_augment=8):
+    """BASELINE config C4 at its own scale: TSP-n POMO = 6-layer instance-norm encoder, no graph
+    context (zoo/pomo/model.py:59-63), dihedral-8 StateAugmentation (aug-major, data/transforms.py:
+    16-38,118-151), multistart greedy with n starts (start-major), then POMO's reductions
+    (pomo/model.py:103-136): max over starts, max over augmentations."""
+    torch.manual_seed(seed)
+    env = make_env("tsp", n, check=True)
+    pol = ref.AttentionModelPolicy(env_name="tsp", num_encoder_layers=6, normalization="instance",
+                                   use_graph_context=False).eval()
+    name_seeded_weights(pol, seed)
+    td0 = env.generator(batch_size=[batch])
+    out = {"inst::locs": npy(td0["locs"]), "weight_seed": np.int64(seed), "num_augment": np.int64(num_augment)}
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        tda = ref.transforms.StateAugmentation(num_augment=num_augment, augment_fn="dihedral8")(td)
+        out["aug_locs"] = npy(tda["locs"])
+        h, _ = pol.encoder(tda)
+        out["h_first_rows"] = npy(h[:2])  # encoder guard: aug 0 of the first two instances
+        o = pol(tda.clone(), env, phase="test", decode_type="multistart_greedy", num_starts=n,
+                return_sum_log_likelihood=False)
+        acts, lp, rew = o["actions"], o["log_likelihood"], o["reward"]
+        assert acts.max() < 256
+        r = ref.ops.unbatchify(rew, (num_augment, n))            # [B, aug, start]
+        max_r, _ = r.max(dim=-1)
+        max_aug_r, _ = max_r.max(dim=1)
+        out.update(actions=npy(acts).astype(np.uint8), logprobs_sum=npy(lp.sum(1)), reward=npy(rew),
+                   logprobs_rows=npy(lp[: 2 * batch]),  # full per-step log-probs of the first rows
+                   max_reward=npy(max_r), max_aug_reward=npy(max_aug_r), reward_b_aug_start=npy(r))
+    return out
+
+
 def layout_fixture():
     torch.manual_seed(11)
     x = torch.rand(3, 5, 2)
@@ -227,6 +294,9 @@ def main():
         "am_cvrp20": lambda: am_fixture("cvrp", 20, 8, 201),
         "am_tsp50": lambda: am_fixture("tsp", 50, 4, 202, ms_batch=2),
         "am_cvrp50": lambda: am_fixture("cvrp", 50, 4, 203, ms_batch=2),
+        "am_tsp100": lambda: am_fixture("tsp", 100, 4, 204, ms_batch=1, lean=True),
+        "am_cvrp100": lambda: am_fixture("cvrp", 100, 4, 205, ms_batch=1, lean=True),
+        "pomo_tsp100": lambda: pomo_fixture(100, 2, 400),
         "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
         "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
         "layout": layout_fixture,

@@ -62,3 +62,46 @@ def test_baseline_allreduce_equals_single_process_mean():
     for _, mean, ref, _ in res:
         assert abs(mean - ref) < 1e-6
     assert res[0][1] == res[1][1]  # identical on both ranks
+
+
+def _grad_worker(rank, world, port, q):
+    import torch.nn as nn
+
+    from rl4co_b200.distributed import rank_stream_offset, sync_gradients
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # identical replicas
+    net = nn.Sequential(nn.Linear(4, 8), nn.ReLU(), nn.Linear(8, 1))
+    frozen = nn.Linear(3, 3)  # a parameter that gets no gradient on any rank
+    opt = torch.optim.SGD(list(net.parameters()) + list(frozen.parameters()), lr=0.1)
+    torch.manual_seed(100 + rank)  # different data per rank
+    x = torch.randn(16, 4)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        net(x).pow(2).mean().backward()
+        n = sync_gradients(list(net.parameters()) + list(frozen.parameters()))
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    q.put((rank, flat.tolist(), n, rank_stream_offset()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_sync_keeps_replicas_identical():
+    """reinforce_step / pomo_step bypass DDP, so they average gradients themselves; after a few
+    steps on different data the replicas' parameters must still be bit-identical."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]
+    assert res[0][2] == res[1][2] > 0
+    assert [r[3] for r in res] == [0, 1]  # distinct Philox streams per rank

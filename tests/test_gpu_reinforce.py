@@ -113,3 +113,28 @@ def test_pomo_step_eval_and_train(env_name):
     opt = torch.optim.Adam(pol.parameters(), lr=1e-4)
     tr = pomo_step(pol, env, td, phase="train", optimizer=opt)
     assert torch.isfinite(tr["loss"])
+
+
+@pytest.mark.parametrize("env_name", ["tsp", "cvrp"])
+def test_policy_forward_under_autograd_is_differentiable(env_name):
+    """`policy(td, env, phase="train")` with autograd on (what the reference's REINFORCE.shared_step
+    does, reinforce.py:59-69) must return a log_likelihood that backpropagates into the policy."""
+    env, pol, td = _setup(env_name, 20, 16)
+    pol.train()
+    out = pol(td, env, phase="train", decode_type="sampling", seed=2)
+    assert out["log_likelihood"].requires_grad
+    loss = -((out["reward"] - out["reward"].mean()) * out["log_likelihood"]).mean()
+    loss.backward()
+    g = pol.decoder.project_node_embeddings.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+    with torch.no_grad():
+        chk = pol(td, env, phase="train", actions=out["actions"])
+    torch.testing.assert_close(out["log_likelihood"].detach(), chk["log_likelihood"], rtol=1e-4, atol=2e-4)
+
+
+def test_low_temperature_takes_the_stepping_path():
+    """2*clip/T beyond exp's fp32 range would flush the fused kernel's fixed-offset softmax to 0."""
+    env, pol, td = _setup("tsp", 20, 8)
+    with torch.no_grad():
+        out = pol(td, env, decode_type="sampling", temperature=0.1)
+    assert torch.isfinite(out["log_likelihood"]).all()

@@ -206,8 +206,16 @@ def test_no_cpu_fallback():
     from rl4co_b200.envs import get_env
 
     env = get_env("cvrp", generator_params=dict(num_loc=10))
+    td = env.reset(batch_size=[4])  # reset only allocates state: works on any device
+    assert td["action_mask"].shape == (4, 11) and not td["action_mask"][:, 0].any() and td["action_mask"][:, 1:].all()
+    td.set("action", torch.ones(4, dtype=torch.int64))
     with pytest.raises(native.NativeLibraryError):
-        env.reset(batch_size=[4])  # CVRP reset needs get_action_mask -> CUDA kernel
+        env.step(td)  # every arithmetic entry point is CUDA-only
+    with pytest.raises(native.NativeLibraryError):
+        env.get_action_mask(td)
+    with pytest.raises(native.NativeLibraryError):
+        get_env("tsp", generator_params=dict(num_loc=5)).get_reward(
+            get_env("tsp", generator_params=dict(num_loc=5)).reset(batch_size=[2]), torch.arange(5).repeat(2, 1))
 
 
 def test_unsupported_options_are_rejected():

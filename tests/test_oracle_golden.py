@@ -8,7 +8,7 @@ from oracle import am_rollout_oracle as O
 from conftest import env_of
 
 ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50"]
-AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50"]
+AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50", "am_tsp100", "am_cvrp100"]
 
 
 @pytest.mark.parametrize("name", ENV_FIX)
@@ -143,3 +143,40 @@ def test_pomo_reduce_and_loss():
     rew = torch.randn(S * B)
     bl = O.shared_baseline(rew, S)
     assert bl.shape == (B, 1)
+
+
+def test_pomo_config_c4_fixture(golden):
+    """BASELINE config C4 at its own scale (TSP-100, 6-layer instance-norm encoder, no graph context, dihedral-8,
+    100 starts): the oracle port reproduces the unmodified reference's POMO forward -- weights are regenerated from
+    parameter names (conftest.name_seeded_weights), so this also pins the state_dict naming."""
+    from conftest import name_seeded_weights
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    g = golden("pomo_tsp100")
+    n_aug, seed = int(g["num_augment"]), int(g["weight_seed"])
+    pol = FusedAttentionModelPolicy(env_name="tsp", num_encoder_layers=6, normalization="instance",
+                                    use_graph_context=False)
+    W = name_seeded_weights(pol.state_dict(), seed)
+    locs = g["inst::locs"]
+    B, N = locs.shape[:2]
+    aug = O.dihedral_8_augmentation(locs)  # StateAugmentation: batchify, keep the first B rows, x8 (transforms.py:40-48)
+    assert torch.equal(aug, g["aug_locs"])
+    with torch.inference_mode():
+        st = O.env_reset("tsp", {"locs": aug})
+        h, _ = O.encoder_forward(W, "tsp", st, num_layers=6, normalization="instance")
+        torch.testing.assert_close(h[:2], g["h_first_rows"], rtol=1e-5, atol=1e-5)
+        ref_actions = g["actions"].long()
+        free = O.rollout(W, "tsp", {"locs": aug}, h, "multistart_greedy", use_graph_context=False, num_starts=N,
+                         faithful_copies=False)
+        same = (free["actions"] == ref_actions).all(1)
+        assert same.float().mean() > 0.97, "free-running POMO trajectories differ beyond near-tie noise"
+        # teacher-forced on the reference's actions (expanded batch; the forced first step carries log-prob 0)
+        out = O.rollout(W, "tsp", {"locs": O.batchify(aug, N)}, O.batchify(h, N), actions=ref_actions,
+                        use_graph_context=False, faithful_copies=False)
+    torch.testing.assert_close(out["logprobs"][:, 1:].sum(1), g["logprobs_sum"], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(out["logprobs"][: g["logprobs_rows"].shape[0], 1:], g["logprobs_rows"][:, 1:],
+                               rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(out["reward"], g["reward"], rtol=1e-6, atol=0)
+    max_r, max_aug = O.pomo_reduce(out["reward"], n_aug, N)[:2]
+    torch.testing.assert_close(max_r, g["max_reward"])
+    torch.testing.assert_close(max_aug, g["max_aug_reward"])

@@ -1,5 +1,5 @@
 """Time + check co_encoder_mha variants against torch SDPA (fp64 reference).
-Usage: B=65536 NS=100 VARIANTS=simt,tc,tc2 python tools/bench_mha.py   (the never-run draft: VARIANTS=tc3-unverified, small B, under `timeout`)"""
+Usage: B=65536 NS=100 VARIANTS=simt,tc,tc2 python tools/bench_mha.py   """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +7,7 @@ import torch.nn.functional as F
 from rl4co_b200 import native
 
 B = int(os.environ.get('B', 65536))
-VARIANTS = os.environ.get('VARIANTS', 'simt,tc,tc2').split(',')
+VARIANTS = os.environ.get('VARIANTS', 'simt,tc,tc2,tc3').split(',')
 
 def t(fn, n=3):
     fn(); torch.cuda.synchronize()
