@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- node-selections/sec of the AM rollout hot path (BASELINE.json metric).
 
-Workload (config.workload): TSP-100 AttentionModel greedy rollout, 65 536 instances per GPU
-(north_star's headline; weak scaling: every rank owns its own 65 536 instances, no data-path
-collective, one 2-double NCCL all-reduce for the REINFORCE mean baseline per step when N>1).
+Workloads (`--workload`, named in config.workload; default = north_star's headline):
+  tsp100  TSP-100 AttentionModel greedy rollout, 65 536 instances PER GPU (weak scaling, BASELINE metric
+          "node-selections/sec TSP-100 AM rollout @1/2/4/8 B200")
+  c2      TSP-50 greedy, 4 096 instances per GPU            (BASELINE configs[1])
+  c3      CVRP-50 sampling (in-kernel Philox), 4 096 per GPU (BASELINE configs[2])
+  c4      TSP-100 POMO: 1 024 instances IN TOTAL x 8 dihedral augmentations x 100 starts, 6-layer
+          instance-norm encoder, no graph context; instances sharded over the ranks (strong scaling)
+  c5      CVRP-100 REINFORCE training step: 65 536 instances IN TOTAL sharded over the ranks (strong):
+          sampling rollout + differentiable log-likelihood + loss + backward + gradient all-reduce +
+          Adam, mean baseline over the GLOBAL batch through one {sum,count} all-reduce
 
-  value : decode path with inputs RESIDENT in HBM (encoder output h + instance data):
-          one step = FusedAttentionModelDecoder._precompute_cache (one tcgen05 3xTF32 GEMM)
-                   + co_rollout (persistent kernel: context + glimpse + pointer + tanh/mask/
-                     log-softmax + arg-max + env step + incremental tour length, all T steps)
-  e2e   : the call a user makes -- policy(td, env, decode_type="greedy") -- from HOST buffers:
-          pinned-host locs -> H2D, encoder (Linear layers on co_gemm_tf32x3, attention on
-          co_encoder_mha), cache GEMM, co_rollout, D2H of actions + reward + log-likelihood.
-  --impl reference : the reference's own algorithm on the host CPU cores (oracle port of the
-          rl4co PyTorch path incl. its per-step K/V/L copies), same metric / config.
+  value : the step with inputs RESIDENT in HBM.
+          rollout workloads: FusedAttentionModelDecoder._precompute_cache (one tcgen05 3xTF32 GEMM) + co_rollout
+          (persistent kernel: context + glimpse + pointer + tanh/mask/log-softmax + selection + env step +
+          incremental tour length, all T steps) from the resident encoder output;
+          c4: cache GEMM + query-batched co_rollout (100 starts share K/V/L) + POMO max reductions;
+          c5: the whole training step from the resident batch.
+  e2e   : the call a user makes, from HOST buffers: pinned-host instance data -> H2D, policy / pomo_step /
+          reinforce_step, D2H of the step's result.
+  --impl reference : the reference's OWN policy (unmodified rl4co files, oracle/ref_runner.py) on the host CPU
+          cores, same metric / workload on a bounded sample, all the host cores it can use.
 
-Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
-ranks.  Inputs (16.8 GB cache, 3.4 GB embeddings per rank) are far larger than the 126 MB L2,
-so no explicit L2 flush is needed between iterations (stated in config).
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The
+resident inputs of the default workload (13.4 GB cache + 3.4 GB embeddings per rank) are far larger than the
+126 MB L2, so no explicit L2 flush is needed between iterations (stated in config).  Outside the timed region a
+parity gate re-checks a 1 024-row slice of the timed batch against the CPU oracle (`parity_gate` in the line).
 """
 
 from __future__ import annotations
@@ -35,9 +44,22 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "node-selections/sec TSP-100 AM rollout"
 UNIT = "selections/s"
 E = 128
+
+WORKLOADS = {
+    "tsp100": dict(env="tsp", n=100, batch=65536, per_gpu=True, decode="greedy", kind="rollout", policy={},
+                   metric="node-selections/sec TSP-100 AM rollout", label="TSP-100 AM greedy rollout"),
+    "c2": dict(env="tsp", n=50, batch=4096, per_gpu=True, decode="greedy", kind="rollout", policy={},
+               metric="node-selections/sec TSP-50 AM rollout", label="TSP-50 AM greedy rollout"),
+    "c3": dict(env="cvrp", n=50, batch=4096, per_gpu=True, decode="sampling", kind="rollout", policy={},
+               metric="node-selections/sec CVRP-50 AM sampling rollout", label="CVRP-50 AM sampling rollout"),
+    "c4": dict(env="tsp", n=100, batch=1024, per_gpu=False, decode="multistart_greedy", kind="pomo",
+               policy=dict(num_encoder_layers=6, normalization="instance", use_graph_context=False),
+               metric="node-selections/sec TSP-100 POMO 8-aug x 100-start", label="TSP-100 POMO 8 aug x 100 starts"),
+    "c5": dict(env="cvrp", n=100, batch=65536, per_gpu=False, decode="sampling", kind="train", policy={},
+               metric="node-selections/sec CVRP-100 AM REINFORCE step", label="CVRP-100 AM REINFORCE training step"),
+}
 
 
 def parse():
@@ -46,13 +68,13 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--env", default="tsp", choices=["tsp", "cvrp"])
-    p.add_argument("--num-loc", type=int, default=100)
-    p.add_argument("--batch", type=int, default=65536, help="instances per GPU")
-    p.add_argument("--decode-type", default="greedy")
-    p.add_argument("--cpu-batch", type=int, default=1024, help="bounded CPU sample (instances)")
+    p.add_argument("--workload", default="tsp100", choices=sorted(WORKLOADS))
+    p.add_argument("--batch", type=int, default=None, help="override the workload's batch (per GPU or total, see workload)")
+    p.add_argument("--cpu-batch", type=int, default=None, help="bounded CPU sample (instances per process)")
+    p.add_argument("--micro-batch", type=int, default=8192, help="c5: instances per differentiable chunk")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-parity-gate", action="store_true")
     return p.parse_args()
 
 
@@ -104,23 +126,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ common
-def make_policy_and_data(env_name, num_loc, batch, rank):
-    from rl4co_b200.envs import get_env
-    from rl4co_b200.policy import FusedAttentionModelPolicy
-
-    torch.manual_seed(0)
-    policy = FusedAttentionModelPolicy(env_name=env_name, embed_dim=128, num_heads=8, num_encoder_layers=3,
-                                       normalization="batch", tanh_clipping=10.0).eval()
-    env = get_env(env_name, generator_params=dict(num_loc=num_loc), check_solution=False)
-    torch.manual_seed(1234 + rank)
-    td_host = env.generator(batch)
-    return policy, env, td_host
+def policy_kwargs(wl):
+    kw = dict(embed_dim=128, num_heads=8, num_encoder_layers=3, normalization="batch", tanh_clipping=10.0)
+    kw.update(wl["policy"])
+    return kw
 
 
-def algorithmic_bytes_per_instance(env_name, N, T):
+def algorithmic_bytes_per_instance(env_name, N, T, S=1):
     """read K,V,L + node table rows, graph ctx, coords (+demand); write
-    actions (int64) + logp (f32) per step, reward + log-likelihood."""
-    b = N * 4 * E * 4 + E * 4 + N * 8 + T * (8 + 4) + 4 + 4
+    actions (int64) + logp (f32) per step and reward + log-likelihood per trajectory (S per instance)."""
+    b = N * 4 * E * 4 + E * 4 + N * 8 + S * (T * (8 + 4) + 4 + 4)
     if env_name == "cvrp":
         b += (N - 1) * 4
     return b
@@ -134,91 +149,117 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(batch):
-    """dram__bytes_read+write of the rollout kernel from the committed `ncu --set full` capture,
-    scaled per instance to this launch (the kernel streams each instance exactly once)."""
+def ncu_traffic(workload, instances):
+    """dram__bytes_read+write of the dominant kernel from the committed `ncu --set full` capture, per instance,
+    scaled to this launch (the kernel streams each instance exactly once)."""
     try:
         with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_instance"] * batch
+            d = json.load(f)
+        if workload in d:
+            return d[workload]["dram_bytes_per_instance"] * instances
+        if workload == "tsp100" and "dram_bytes_per_instance" in d:
+            return d["dram_bytes_per_instance"] * instances
     except Exception:
-        return None
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(env_name, num_loc, batch, decode_type, steps, warmup):
-    """The reference's algorithm on the host cores: oracle port (the reference is Python and
-    cannot travel to this box; the port is pinned to it by tests/golden)."""
-    from oracle import am_rollout_oracle as O
+def cpu_reference(wl, batch, steps, warmup, multi_process=True):
+    from oracle import ref_runner
 
-    cores = os.cpu_count() or 1
-    torch.manual_seed(0)
-    from rl4co_b200.policy import FusedAttentionModelPolicy
-
-    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=3).eval()
-    W = {k: v.detach() for k, v in pol.state_dict().items()}
-    # give the reference its best thread count: torch CPU ops on [B,N,128] tensors stop scaling
-    # (and regress) well below a 100+-core host's full width
-    probe = O.generate_instances(env_name, min(256, batch), num_loc)
-    best = (None, float("inf"))
-    with torch.inference_mode():
-        for nt in sorted({min(c, cores) for c in (8, 16, 32, 64)}):  # the full width of a 100+-core host is far slower
-            torch.set_num_threads(nt)
-            st0 = O.env_reset(env_name, probe)
-            h, _ = O.encoder_forward(W, env_name, st0, num_layers=3)
-            O.rollout(W, env_name, probe, h, decode_type=decode_type, faithful_copies=True)  # warm
-            t0 = time.perf_counter()
-            st0 = O.env_reset(env_name, probe)
-            h, _ = O.encoder_forward(W, env_name, st0, num_layers=3)
-            O.rollout(W, env_name, probe, h, decode_type=decode_type, faithful_copies=True)
-            dt = time.perf_counter() - t0
-            if dt < best[1]:
-                best = (nt, dt)
-    torch.set_num_threads(best[0])
-    torch.manual_seed(1234)
-    inst = O.generate_instances(env_name, batch, num_loc)
-    times, dec_times, nsel = [], [], 0
-    with torch.inference_mode():
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            st0 = O.env_reset(env_name, inst)
-            h, _ = O.encoder_forward(W, env_name, st0, num_layers=3)
-            t1 = time.perf_counter()
-            out = O.rollout(W, env_name, inst, h, decode_type=decode_type, faithful_copies=True)
-            t2 = time.perf_counter()
-            if it >= warmup:
-                times.append(t2 - t0); dec_times.append(t2 - t1)
-            nsel = out["actions"].numel()
-    return {"selections": nsel, "policy_forward_s": sum(times) / len(times), "decode_only_s": sum(dec_times) / len(dec_times),
-            "cores": torch.get_num_threads(), "host_cores": cores, "threads": torch.get_num_threads()}
+    dk = {}
+    if wl["kind"] == "pomo":
+        dk = {"num_starts": wl["n"]}
+    return ref_runner.time_reference(wl["env"], wl["n"], batch, wl["decode"], steps=steps, warmup=warmup,
+                                     policy_kwargs=wl["policy"], decode_kwargs=dk, multi_process=multi_process,
+                                     augment=8 if wl["kind"] == "pomo" else 0, train=wl["kind"] == "train")
 
 
-def run_reference(args):
+def cpu_sample_batch(wl, override):
+    if override:
+        return override
+    return {"rollout": 1024 if wl["n"] >= 100 else 2048, "pomo": 2, "train": 256}[wl["kind"]]
+
+
+def cpu_baseline_obj(wl, r):
+    scope = {"rollout": "policy-forward (encoder + decode loop + reward)",
+             "pomo": "dihedral-8 augmentation + policy-forward multistart greedy",
+             "train": "policy-forward sampling + REINFORCE loss + backward + Adam"}[wl["kind"]]
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores_used"], "kind": r["kind"],
+            "sample": f"{wl['label']}, {scope}; {r['batch_per_step']} instances per step, torch CPU fp32, "
+                      f"{r['layout']} on a {r['host_cores']}-core host (better of 1 process with its best thread count "
+                      f"and P processes x T threads over all cores)",
+            "single_process": r["single"], "multi_process": r.get("multi")}
+
+
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.env, args.num_loc, args.cpu_batch, args.decode_type, args.steps, min(args.warmup, 1))
-    val = r["selections"] / r["policy_forward_s"]
-    sample = (f"{args.env.upper()}-{args.num_loc} {args.decode_type} policy-forward (encoder+decode+reward), "
-              f"B={args.cpu_batch} per step, torch CPU fp32, {r['threads']} threads (best of 8/16/32/64 on a {r['host_cores']}-core host)")
+    r = cpu_reference(wl, cpu_sample_batch(wl, args.cpu_batch), steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": r["policy_forward_s"] * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.env.upper()}-{args.num_loc} AM {args.decode_type} rollout (reference algorithm, CPU)",
-                   "batch_per_step": args.cpu_batch, "scope": "policy-forward"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
-                         "decode_only_value": r["selections"] / r["decode_only_s"]},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": wl["metric"], "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak" if wl["per_gpu"] else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{wl['label']} (the reference's own rl4co files on the host CPU)",
+                   "batch_per_step": r["batch_per_step"], "scope": "policy-forward"},
+        "cpu_baseline": cpu_baseline_obj(wl, r),
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------ parity gate
+def parity_gate(wl, policy, td_dev, h, res, rows=1024):
+    """Outside the timed region: a `rows`-row slice of the batch that was just timed, against the CPU oracle
+    (decode path from the GPU's own encoder output): teacher-forced log-likelihood / reward (<= 1e-5 relative,
+    2e-5 absolute floor per log-prob) and, for greedy, the number of free-running trajectories that differ
+    (near-tie flips).  Rows are the first `rows` instances (S = 1 workloads)."""
+    from oracle import am_rollout_oracle as O
+
+    env_name = wl["env"]
+    rows = min(rows, h.shape[0])
+    W = {k: v.detach().cpu() for k, v in policy.state_dict().items()}
+    inst = {k: td_dev[k][:rows].cpu() for k in ("locs", "demand") if k in td_dev.keys()}
+    if env_name == "cvrp":
+        inst["depot"], inst["locs"] = inst["locs"][:, 0], inst["locs"][:, 1:]
+    hh = h[:rows].cpu()
+    acts = res["actions"][:rows].cpu()
+    T = int(res["steps"][:rows].max().item())
+    acts = acts[:, :T]
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    ugc = wl["policy"].get("use_graph_context", True)
+    with torch.inference_mode():
+        ref = O.rollout(W, env_name, inst, hh, actions=acts, use_graph_context=ugc, faithful_copies=False)
+        free = O.rollout(W, env_name, inst, hh, "greedy", use_graph_context=ugc, faithful_copies=False) \
+            if wl["decode"] == "greedy" else None
+    lp_gpu, lp_ref = res["logprobs"][:rows, :T].cpu(), ref["logprobs"]
+    rw_gpu, rw_ref = res["reward"][:rows].cpu(), ref["reward"]
+    lp_err = (lp_gpu - lp_ref).abs()
+    lp_ok = bool((lp_err <= 1e-5 * lp_ref.abs() + 2e-5).all())
+    rw_rel = ((rw_gpu - rw_ref).abs() / rw_ref.abs()).max().item()
+    out = {"rows": rows, "checker": "oracle port (oracle/am_rollout_oracle.py), teacher-forced on the GPU's actions",
+           "max_abs_logp_err": lp_err.max().item(), "max_rel_reward_err": rw_rel, "logp_ok": lp_ok,
+           "reward_ok": rw_rel <= 1e-5, "ok": lp_ok and rw_rel <= 1e-5}
+    if free is not None:
+        same = (free["actions"][:, :T] == acts).all(1) if free["actions"].shape[1] >= T else torch.zeros(rows, dtype=torch.bool)
+        out["free_running_rows_differing"] = int((~same).sum())
+        out["free_running_flip_fraction"] = float((~same).float().mean())
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def run_ours(args, wl):
     import torch.distributed as dist
 
     from rl4co_b200 import native
+    from rl4co_b200.distributed import shard_bounds
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+    from rl4co_b200.tensordict import TensorDict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,13 +272,24 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     native.lib()
 
-    env_name, n, B = args.env, args.num_loc, args.batch
+    env_name, n, kind = wl["env"], wl["n"], wl["kind"]
+    total = args.batch if args.batch else wl["batch"]
+    if wl["per_gpu"]:
+        B, global_batch = total, total * world
+    else:
+        lo, hi = shard_bounds(total, rank, world)
+        B, global_batch = hi - lo, total
     N = n + (1 if env_name == "cvrp" else 0)
-    policy, env, td_host = make_policy_and_data(env_name, n, B, rank)
-    policy = policy.to(dev)
 
+    torch.manual_seed(0)
+    policy = FusedAttentionModelPolicy(env_name=env_name, **policy_kwargs(wl)).to(dev)
+    policy = policy.train() if kind == "train" else policy.eval()
+    env = get_env(env_name, generator_params=dict(num_loc=n), check_solution=False)
+    torch.manual_seed(1234 + rank)
+    td_host = env.generator(B)
     pinned = {k: td_host[k].pin_memory() for k in td_host.keys()}
     stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev)
 
     def barrier():
         if world > 1:
@@ -245,63 +297,146 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def baseline_allreduce(reward):
-        """REINFORCE mean baseline over the GLOBAL batch: {sum, count} in f64 (north_star)."""
+        """REINFORCE mean baseline over the GLOBAL batch: {sum, count} in f64 (north_star).  The next step does
+        not depend on it, so the NCCL all-reduce runs on a side stream and overlaps the next step's kernels
+        (round 1 had it stream-serialised behind every rollout: every rank waited for the slowest rank)."""
         stats.zero_()
         native.reward_stats(reward, stats)
         if world > 1:
-            dist.all_reduce(stats)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_reduce(stats)
         return stats
 
-    # ---- resident inputs for `value`
-    from rl4co_b200.tensordict import TensorDict
-
-    with torch.inference_mode():
-        td_dev = env.reset(TensorDict({k: v.to(dev) for k, v in pinned.items()}, batch_size=[B]))
-        h, _ = policy.encoder(td_dev)
-        h = h.contiguous()
-    torch.cuda.synchronize()
+    def join_side():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)
 
     rollout_ev = []
+    host_out = {}
 
-    def decode_step(record=False):
-        """hot path from resident h: cache GEMM + persistent rollout (+ baseline all-reduce)."""
+    def to_host(name, t):
+        if name not in host_out or host_out[name].shape != t.shape:
+            host_out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host_out[name].copy_(t, non_blocking=True)
+
+    def h2d():
+        return TensorDict({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}, batch_size=[B])
+
+    # ------------------------------------------------------------------ workload-specific steps
+    gate_ctx = {}
+    if kind == "rollout":
         with torch.inference_mode():
-            cached = policy.decoder._precompute_cache(h)
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            res = native.rollout(env_name, native.SELECT_GREEDY if "greedy" in args.decode_type else native.SELECT_SAMPLE_PHILOX,
-                                 cached.rollout_cache, cached.graph_context_or_none, cached.q_placeholder,
-                                 cached.w_capacity, td_dev["locs"], td_dev["demand"] if env_name == "cvrp" else None,
-                                 td_dev["vehicle_capacity"].reshape(-1) if env_name == "cvrp" else None, B, N,
-                                 tanh_clipping=10.0, seed=1)
-            if record:
-                e1.record()
-                rollout_ev.append((e0, e1))
-            baseline_allreduce(res["reward"])
-        return res
+            td_dev = env.reset(TensorDict({k: v.to(dev) for k, v in pinned.items()}, batch_size=[B]))
+            h, _ = policy.encoder(td_dev)
+            h = h.contiguous()
+        mode = native.SELECT_GREEDY if "greedy" in wl["decode"] else native.SELECT_SAMPLE_PHILOX
+        v3 = os.environ.get("CO_ROLLOUT_IMPL") == "v3"
 
-    host_out = {}  # pinned result buffers, reused across steps (a pageable destination is copied through a bounce buffer)
+        def value_step(record=False):
+            with torch.inference_mode():
+                cached = policy.decoder._precompute_cache(h, first_table=v3)
+                if record:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                res = native.rollout(env_name, mode, cached.rollout_cache, cached.graph_context_or_none,
+                                     cached.q_placeholder, cached.w_capacity, td_dev["locs"],
+                                     td_dev["demand"] if env_name == "cvrp" else None,
+                                     td_dev["vehicle_capacity"].reshape(-1) if env_name == "cvrp" else None, B, N,
+                                     tanh_clipping=10.0, seed=1, node_emb=h if env_name == "tsp" else None,
+                                     w_first=cached.w_first)
+                if record:
+                    e1.record()
+                    rollout_ev.append((e0, e1))
+                baseline_allreduce(res["reward"])
+            return res
 
-    def e2e_step():
+        def e2e_step():
+            with torch.inference_mode():
+                td = env.reset(h2d())
+                out = policy(td, env, phase="test", decode_type=wl["decode"], **({"seed": 1} if "sampling" in wl["decode"] else {}))
+                baseline_allreduce(out["reward"])
+                for k in ("actions", "reward", "log_likelihood"):
+                    to_host(k, out[k])
+                join_side()
+                torch.cuda.current_stream().synchronize()  # the results are on the host when the step returns
+            return ("actions", "reward", "log_likelihood")
+
+        gate_ctx = dict(td=td_dev, h=h)
+        S_kernel, kernel_name, scope = 1, "co::hw::rollout_kernel", \
+            "precompute_cache GEMM + persistent rollout kernel from resident encoder output"
+    elif kind == "pomo":
+        from rl4co_b200.ops import StateAugmentation, unbatchify
+        from rl4co_b200.reinforce import pomo_step
+
+        n_aug, n_start = 8, n
         with torch.inference_mode():
-            td = TensorDict({k: v.to(dev, non_blocking=True) for k, v in pinned.items()}, batch_size=[B])
-            td = env.reset(td)
-            out = policy(td, env, phase="test", decode_type=args.decode_type)
-            baseline_allreduce(out["reward"])
-            for k in ("actions", "reward", "log_likelihood"):
-                if k not in host_out or host_out[k].shape != out[k].shape:
-                    host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
-                host_out[k].copy_(out[k], non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the results are on the host when the step returns
-        return host_out
+            td_dev = env.reset(TensorDict({k: v.to(dev) for k, v in pinned.items()}, batch_size=[B]))
+            td_aug = StateAugmentation(num_augment=n_aug)(td_dev)
+            h, _ = policy.encoder(td_aug)
+            h = h.contiguous()
+
+        def value_step(record=False):
+            with torch.inference_mode():
+                cached = policy.decoder._precompute_cache(h, first_table=True)
+                if record:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                res = native.rollout(env_name, native.SELECT_GREEDY, cached.rollout_cache, None, cached.q_placeholder,
+                                     None, td_aug["locs"], None, None, n_aug * B, N, num_starts=n_start,
+                                     forced_start=True, num_loc=n, tanh_clipping=10.0)
+                if record:
+                    e1.record()
+                    rollout_ev.append((e0, e1))
+                r = unbatchify(res["reward"], (n_aug, n_start))  # pomo/model.py:103-136
+                res["max_aug_reward"] = r.max(-1)[0].max(1)[0]
+            return res
+
+        def e2e_step():
+            td = env.reset(h2d())
+            out = pomo_step(policy, env, td, num_augment=n_aug, num_starts=n_start, phase="test")
+            with torch.inference_mode():
+                to_host("reward", out["reward"])
+                to_host("max_aug_reward", out["max_aug_reward"])
+                torch.cuda.current_stream().synchronize()
+            return ("reward", "max_aug_reward")
+
+        S_kernel, kernel_name, scope = n_start, "co::rollout_ms_kernel", \
+            "precompute_cache GEMM + query-batched rollout kernel (100 starts share K/V/L) + POMO max reductions"
+    else:  # train
+        from rl4co_b200.reinforce import get_reinforce_baseline, reinforce_step
+
+        opt = torch.optim.Adam(policy.parameters(), lr=1e-4)
+        bl = get_reinforce_baseline("mean")
+        td_dev = env.reset(TensorDict({k: v.to(dev) for k, v in pinned.items()}, batch_size=[B]))
+        step_no = [0]
+
+        def value_step(record=False, td=None):
+            step_no[0] += 1
+            return reinforce_step(policy, env, td_dev if td is None else td, bl, opt, seed=step_no[0],
+                                  micro_batch=args.micro_batch, matmul_precision="medium")
+
+        def e2e_step():
+            out = value_step(td=env.reset(h2d()))
+            to_host("loss", out["loss"].reshape(1))
+            to_host("reward_mean", out["reward"].mean().reshape(1))
+            torch.cuda.current_stream().synchronize()
+            return ("loss", "reward_mean")
+
+        S_kernel, kernel_name, scope = 1, "co::hw::rollout_kernel", \
+            ("whole REINFORCE step from the resident batch: sampling rollout (persistent kernel) + differentiable "
+             "teacher-forced log-likelihood + loss + backward + gradient all-reduce + Adam; autograd GEMMs at "
+             "float32_matmul_precision('medium') like the reference trainer (rl4co/utils/trainer.py:89-90)")
 
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
-        res = decode_step()
+        res = value_step()
+    join_side()
     torch.cuda.synchronize()
-    T_steps = res["steps"].sum().item()  # exact number of (decode -> select -> env.step) iterations
-    sel_per_step_rank = float(T_steps)
+    if kind == "train":
+        sel_per_step_rank = float(res["actions"].numel()) if "steps" not in res else float(res["steps"].sum().item())
+    else:
+        sel_per_step_rank = float(res["steps"].sum().item())  # exact number of (decode -> select -> env.step) iterations
 
     # ---- timed: value
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -311,13 +446,14 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        decode_step(record=True)
+        res = value_step(record=True) if kind != "train" else value_step()
+    join_side()
     ev1.record()
     barrier()
     t_mark1 = sampler.mark() if sampler else 0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
-    n_launch = native.LAUNCH_COUNT - launch0  # libcorollout kernels: cache GEMM + rollout + reward stats per step
+    n_launch = native.LAUNCH_COUNT - launch0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     sel = torch.tensor([sel_per_step_rank], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,8 +462,12 @@ def run_ours(args):
     ms_total = t.item()
     sel_total_per_step = sel.item()
     value = sel_total_per_step * args.steps / (ms_total * 1e-3)
-    k_ms = sorted(a.elapsed_time(b) for a, b in rollout_ev)
-    k_ms_avg = sum(k_ms) / len(k_ms)
+    if kind == "train":
+        torch.cuda.synchronize()
+        k_ms_avg = res["rollout_events"][0].elapsed_time(res["rollout_events"][1]) if "rollout_events" in res else float("nan")
+    else:
+        k_ms = sorted(a.elapsed_time(b) for a, b in rollout_ev)
+        k_ms_avg = sum(k_ms) / len(k_ms)
 
     # ---- timed: e2e
     e2e = None
@@ -338,19 +478,30 @@ def run_ours(args):
         launch1 = native.LAUNCH_COUNT
         ev0.record()
         for _ in range(args.steps):
-            host = e2e_step()
+            keys = e2e_step()
         ev1.record()
         barrier()
         e2e_launches = native.LAUNCH_COUNT - launch1
         t2 = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-        d2h = sum(v.numel() * v.element_size() for v in host.values())
+        h2d_b = sum(v.numel() * v.element_size() for v in pinned.values())
+        d2h_b = sum(host_out[k].numel() * host_out[k].element_size() for k in keys)
         e2e = {"value": sel_total_per_step * args.steps / (t2.item() * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t2.item() / args.steps,
-               "gpu_launches": e2e_launches,
-               "scope": "policy(td_host, env): H2D + encoder + cache GEMM + rollout + D2H(actions,reward,ll)"}
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": t2.item() / args.steps,
+               "gpu_launches": e2e_launches, "d2h": list(keys),
+               "scope": {"rollout": "policy(td_host, env): H2D + encoder + cache GEMM + rollout + D2H(actions,reward,ll)",
+                         "pomo": "pomo_step(td_host): H2D + dihedral-8 + 6-layer encoder + cache GEMM + multistart rollout + "
+                                 "max reductions + D2H(reward[B,8,100], max_aug_reward)",
+                         "train": "reinforce_step(td_host): H2D + full training step + D2H(loss, mean reward)"}[kind]}
+
+    # ---- parity gate (outside the timed region, rank 0)
+    gate = None
+    if rank == 0 and kind == "rollout" and not args.no_parity_gate:
+        try:
+            gate = parity_gate(wl, policy, gate_ctx["td"], gate_ctx["h"], res)
+        except Exception as exc:  # the gate must never hide the measurement; it reports its own failure
+            gate = {"ok": False, "error": repr(exc)}
 
     if rank != 0:
         if world > 1:
@@ -358,36 +509,48 @@ def run_ours(args):
         return
 
     peak, peak_kind = measured_peaks()
-    T_inst = N if env_name == "tsp" else None
-    bytes_per_launch = algorithmic_bytes_per_instance(env_name, N, N if env_name == "tsp" else sel_per_step_rank / B) * B
-    achieved = bytes_per_launch / (k_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "co::rollout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                "traffic": ncu_traffic(B) if (env_name == "tsp" and n == 100) else None, "kernel_ms": k_ms_avg, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel_share_of_step": k_ms_avg * args.steps / ms_total,
-                "note": "latency/issue-bound on-chip loop; HBM roofline shown as required, see DESIGN.md"}
+    inst_kernel = B * (8 if kind == "pomo" else 1)
+    T_avg = sel_per_step_rank / (inst_kernel * S_kernel)
+    roofline = None
+    if kind != "train":
+        bytes_per_launch = algorithmic_bytes_per_instance(env_name, N, T_avg, S_kernel) * inst_kernel
+        achieved = bytes_per_launch / (k_ms_avg * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                    "traffic": ncu_traffic(args.workload, inst_kernel), "kernel_ms": k_ms_avg,
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "kernel_share_of_step": k_ms_avg * args.steps / ms_total,
+                    "cycles_per_selection_per_sm": (k_ms_avg * 1e-3 * (clocks["sm_mhz"] or 1965.0) * 1e6 * 148
+                                                    / sel_per_step_rank) if clocks else None,
+                    "note": "latency/issue-bound on-chip loop (one instance per SM); HBM roofline shown as required, "
+                            "see DESIGN.md 4.1"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(env_name, n, args.cpu_batch, args.decode_type, steps=2, warmup=1)
-        cpu_baseline = {
-            "value": r["selections"] / r["policy_forward_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": f"{env_name.upper()}-{n} {args.decode_type} policy-forward, B={args.cpu_batch}, torch CPU fp32, "
-                      f"{r['threads']} threads (best of 8/16/32/64 on a {r['host_cores']}-core host), mean of 2 after 1 warm-up",
-            "decode_only_value": r["selections"] / r["decode_only_s"]}
+        try:
+            r = cpu_reference(wl, cpu_sample_batch(wl, args.cpu_batch), steps=2, warmup=1)
+            cpu_baseline = cpu_baseline_obj(wl, r)
+        except Exception as exc:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{env_name.upper()}-{n} AM {args.decode_type} rollout, batch {B} per GPU",
-                   "global_batch": B * world, "nodes": N, "parallelism": f"dp{world} (instances sharded, no data-path collective)",
-                   "value_scope": "precompute_cache GEMM + persistent rollout kernel from resident encoder output",
-                   "l2_policy": "inputs (16.8 GB cache/rank) exceed L2; no flush needed",
-                   "policy": "AttentionModelPolicy E=128 H=8 L=3 batch-norm random-init seed 0, eval"},
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak" if wl["per_gpu"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl['label']}, " + (f"batch {B} per GPU" if wl["per_gpu"] else f"{global_batch} instances sharded over {world} GPU(s)"),
+                   "workload_key": args.workload, "global_batch": global_batch, "nodes": N,
+                   "parallelism": f"dp{world} (instances sharded, no data-path collective; "
+                                  + ("baseline {sum,count} + gradient all-reduce" if kind == "train" else "baseline {sum,count} all-reduce on a side stream") + ")",
+                   "value_scope": scope,
+                   "l2_policy": "resident inputs per rank exceed the 126 MB L2; no flush needed",
+                   "policy": f"AttentionModelPolicy E=128 H=8 {policy_kwargs(wl)} random-init seed 0"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "selections_per_step": sel_total_per_step,
+        "selections_per_step": sel_total_per_step, "parity_gate": gate,
     }
+    if kind == "train":
+        line["train_step"] = {"sampling_phase_ms": k_ms_avg, "micro_batch": args.micro_batch,
+                              "chunks": res.get("chunks"), "loss": float(res["loss"]),
+                              "collectives": "NCCL all-reduce {sum,count} f64 (baseline) + one flat gradient all-reduce (2.8 MB)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -395,10 +558,11 @@ def run_ours(args):
 
 def main():
     args = parse()
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -184,9 +184,16 @@ typedef struct co_rollout_args {
   int32_t* steps_out;        /* [B_traj]  decode steps until done (incl. forced start) */
   int32_t* max_steps_out;    /* [1] device int32, caller-zeroed: max over trajectories */
   float* used_capacity_out;  /* [B_traj] final used capacity (cvrp) or NULL            */
+  /* round 2: narrow tsp cache (no first-node table) -- the first-node half of project_context
+   * (context.py:129-133) becomes one 128x128 GEMV per episode inside the kernel            */
+  const float* node_emb;     /* [B_inst, N, E] encoder output; tsp with cache_width 4E  */
+  const float* w_first;      /* [E, E] = project_context.weight[:, :E] row-major; same   */
+  int32_t cache_width;       /* floats per row of `cache`: 4E, or 5E = tsp layout with   */
+                             /* the first-node table; 0 = co_cache_width(env_kind)       */
+  int32_t reserved0;
 } co_rollout_args;
 
-int co_cache_width(int env_kind); /* floats per node row of the rollout cache */
+int co_cache_width(int env_kind); /* floats per node row of the widest rollout cache layout (tsp 5E, cvrp 4E) */
 /* largest N the persistent kernel is instantiated for (else CO_ERR_UNSUPPORTED) */
 int co_rollout_max_nodes(void);
 int co_rollout(const co_rollout_args* args, void* stream);

@@ -35,8 +35,11 @@ def _policy_kwargs(workload_kwargs):
     return kw
 
 
-def _build(env_name, num_loc, policy_kwargs):
-    """-> (kind, run(batch) -> selections) using the real reference when available."""
+def _build(env_name, num_loc, policy_kwargs, augment=0, train=False):
+    """-> (kind, make_batch, run(batch) -> selections) using the real reference when available.
+    `augment` = 8: dihedral-8 StateAugmentation before the policy (POMO val/test, pomo/model.py:97-101);
+    `train`: policy-forward in train mode with autograd + REINFORCE loss (mean baseline) + backward + Adam step
+    (reinforce.py:59-111; the Lightning module around it is not needed for the arithmetic)."""
     import torch
 
     if ROOT not in sys.path:
@@ -48,15 +51,28 @@ def _build(env_name, num_loc, policy_kwargs):
         Env = ref.TSPEnv if env_name == "tsp" else ref.CVRPEnv
         env = Env(generator_params=dict(num_loc=num_loc), check_solution=False)
         torch.manual_seed(0)
-        policy = ref.AttentionModelPolicy(env_name=env_name, **policy_kwargs).eval()
+        policy = ref.AttentionModelPolicy(env_name=env_name, **policy_kwargs)
+        policy = policy.train() if train else policy.eval()
+        opt = torch.optim.Adam(policy.parameters(), lr=1e-4) if train else None
+        aug = ref.transforms.StateAugmentation(num_augment=augment, augment_fn="dihedral8") if augment else None
 
         def make_batch(batch, seed):
             torch.manual_seed(seed)
             return env.generator(batch_size=[batch])
 
         def run(td0, decode_type, **kw):
+            if train:
+                out = policy(env.reset(td0.clone()), env, phase="train", decode_type=decode_type, **kw)
+                loss = -((out["reward"] - out["reward"].mean()) * out["log_likelihood"]).mean()
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return out["actions"].numel()
             with torch.inference_mode():
-                out = policy(env.reset(td0.clone()), env, phase="test", decode_type=decode_type, **kw)
+                td = env.reset(td0.clone())
+                if aug is not None:
+                    td = aug(td)
+                out = policy(td, env, phase="test", decode_type=decode_type, **kw)
             return out["actions"].numel()
 
         return "reference", make_batch, run
@@ -74,19 +90,23 @@ def _build(env_name, num_loc, policy_kwargs):
         return O.generate_instances(env_name, batch, num_loc)
 
     def run(inst, decode_type, **kw):
+        if augment or train:
+            raise RuntimeError("the oracle-port fallback only times plain policy-forward workloads")
         with torch.inference_mode():
-            out = O.policy_forward(W, env_name, inst, num_layers=nl, decode_type=decode_type, faithful_copies=True)
+            out = O.policy_forward(W, env_name, inst, num_layers=nl, decode_type=decode_type, faithful_copies=True,
+                                   normalization=policy_kwargs.get("normalization", "batch"))
         return out["actions"].numel()
 
     return "port", make_batch, run
 
 
-def worker(env_name, num_loc, batch, decode_type, steps, warmup, threads, seed, policy_kwargs, decode_kwargs):
+def worker(env_name, num_loc, batch, decode_type, steps, warmup, threads, seed, policy_kwargs, decode_kwargs,
+           augment=0, train=False):
     """One process: `warmup` untimed + `steps` timed policy-forward calls. Returns a dict."""
     import torch
 
     torch.set_num_threads(threads)
-    kind, make_batch, run = _build(env_name, num_loc, _policy_kwargs(policy_kwargs))
+    kind, make_batch, run = _build(env_name, num_loc, _policy_kwargs(policy_kwargs), augment, train)
     td0 = make_batch(batch, seed)
     for _ in range(warmup):
         run(td0, decode_type, **(decode_kwargs or {}))
@@ -101,10 +121,11 @@ def worker(env_name, num_loc, batch, decode_type, steps, warmup, threads, seed, 
             "threads": threads}
 
 
-def _spawn(env_name, num_loc, batch, decode_type, steps, warmup, threads, seed, policy_kwargs, decode_kwargs):
+def _spawn(env_name, num_loc, batch, decode_type, steps, warmup, threads, seed, policy_kwargs, decode_kwargs,
+           augment=0, train=False):
     spec = json.dumps(dict(env_name=env_name, num_loc=num_loc, batch=batch, decode_type=decode_type, steps=steps,
                            warmup=warmup, threads=threads, seed=seed, policy_kwargs=policy_kwargs,
-                           decode_kwargs=decode_kwargs))
+                           decode_kwargs=decode_kwargs, augment=augment, train=train))
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads), CUDA_VISIBLE_DEVICES="")
     return subprocess.Popen([sys.executable, os.path.abspath(__file__), spec], stdout=subprocess.PIPE,
                             stderr=subprocess.DEVNULL, text=True, env=env, cwd=ROOT)
@@ -122,7 +143,7 @@ def _collect(procs):
 
 
 def time_reference(env_name, num_loc, batch, decode_type, steps=2, warmup=1, policy_kwargs=None,
-                   decode_kwargs=None, multi_process=True):
+                   decode_kwargs=None, multi_process=True, augment=0, train=False):
     """Whole-host throughput of the reference policy-forward. Returns a dict for bench.py."""
     cores = os.cpu_count() or 1
     # (1) one process: probe the intra-op thread count on a small batch
@@ -130,12 +151,12 @@ def time_reference(env_name, num_loc, batch, decode_type, steps=2, warmup=1, pol
     best_t, best_rate = cand[0], 0.0
     for nt in cand:
         r = _collect([_spawn(env_name, num_loc, min(128, batch), decode_type, 1, 1, nt, 99, policy_kwargs,
-                             decode_kwargs)])[0]
+                             decode_kwargs, augment, train)])[0]
         rate = r["selections"] / sum(r["step_s"])
         if rate > best_rate:
             best_t, best_rate = nt, rate
     single = _collect([_spawn(env_name, num_loc, batch, decode_type, steps, warmup, best_t, 1234, policy_kwargs,
-                              decode_kwargs)])[0]
+                              decode_kwargs, augment, train)])[0]
     single_rate = single["selections"] / sum(single["step_s"])
     res = {"kind": single["kind"], "host_cores": cores, "single": {"threads": best_t, "value": single_rate,
                                                                  "ms_per_step": 1e3 * sum(single["step_s"]) / steps,
@@ -145,7 +166,7 @@ def time_reference(env_name, num_loc, batch, decode_type, steps=2, warmup=1, pol
         T = 16 if cores >= 32 else 8
         P = max(1, cores // T)
         procs = [_spawn(env_name, num_loc, batch, decode_type, steps, warmup, T, 1234 + i, policy_kwargs,
-                        decode_kwargs) for i in range(P)]
+                        decode_kwargs, augment, train) for i in range(P)]
         outs = _collect(procs)
         # every worker runs the same amount of work concurrently: aggregate = total / slowest worker's timed span
         span = max(sum(o["step_s"]) for o in outs)

@@ -140,6 +140,11 @@ def install() -> None:
             for key in ("done", "terminated"):
                 if key not in out.keys():
                     out.set(key, torch.zeros((*bs, 1), dtype=torch.bool, device=dev))
+            # torchrl returns the reset state on the env's device (RL4COEnvBase.reset moved the env to
+            # td.device just before, envs/common/base.py:141): tensors `_reset` built without `device=`
+            # (tsp/env.py:110) follow, and td.device is set -- select_start_nodes (utils/ops.py:141) relies on it
+            if dev is not None:
+                out = out.to(dev)
             return out
 
     tr = _mod("torchrl")

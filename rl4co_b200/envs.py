@@ -116,6 +116,8 @@ class FusedEnvBase:
         for key in ("done", "terminated"):
             if key not in out.keys():
                 out.set(key, torch.zeros((*batch_size, 1), dtype=torch.bool, device=td.device))
+        if td.device is not None:  # the reset state carries the device explicitly, like torchrl's
+            out = out.to(td.device)
         return out
 
     def get_reward(self, td: TensorDict, actions: torch.Tensor, check_solution: bool | None = None) -> torch.Tensor:

@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
 SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu"]
-HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
+HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_hw_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
@@ -56,6 +56,7 @@ class RolloutArgs(Structure):
         ("forced_actions", c_void_p), ("noise", c_void_p), ("seed", c_uint64), ("offset", c_uint64),
         ("actions_out", c_void_p), ("logp_out", c_void_p), ("reward_out", c_void_p), ("loglik_out", c_void_p),
         ("steps_out", c_void_p), ("max_steps_out", c_void_p), ("used_capacity_out", c_void_p),
+        ("node_emb", c_void_p), ("w_first", c_void_p), ("cache_width", c_int32), ("reserved0", c_int32),
     ]
 
 
@@ -336,8 +337,10 @@ def reward_stats(reward, out2):
 @_on_device_of_first_tensor
 def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, locs, demand, vehicle_capacity,
             B_inst, N, num_starts=1, forced_start=False, num_loc=0, T_max=None, forced_actions=None, noise=None,
-            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0):
-    """Launch the persistent rollout kernel; returns dict of device tensors (no host sync)."""
+            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0, node_emb=None, w_first=None):
+    """Launch the persistent rollout kernel; returns dict of device tensors (no host sync).
+    `cache` is [B_inst, N, W]: W = 4E ([K | V | L' | cur-table]; tsp then needs `node_emb` [B_inst, N, E] and
+    `w_first` [E, E] for the per-episode first-node GEMV) or, tsp only, 5E (with the first-node table)."""
     dev = cache.device
     S = max(1, int(num_starts))
     B_traj = B_inst * S
@@ -368,8 +371,17 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
     a.reward_out, a.loglik_out = _ptr(reward, F32, "reward"), _ptr(loglik, F32, "loglik")
     a.steps_out, a.max_steps_out = _ptr(steps, I32, "steps"), _ptr(max_steps, I32, "max_steps")
     a.used_capacity_out = _ptr(used_out, F32, "used_out")
-    if cache.shape != (B_inst, N, cache_width(env_name)):
-        raise ValueError(f"cache shape {tuple(cache.shape)} != {(B_inst, N, cache_width(env_name))}")
+    W = cache.shape[-1]
+    ok_w = (4 * EMBED_DIM, 5 * EMBED_DIM) if env_name == "tsp" else (4 * EMBED_DIM,)
+    if cache.dim() != 3 or tuple(cache.shape[:2]) != (B_inst, N) or W not in ok_w:
+        raise ValueError(f"cache shape {tuple(cache.shape)} != ({B_inst}, {N}, {' | '.join(map(str, ok_w))})")
+    if env_name == "tsp" and W == 4 * EMBED_DIM:
+        if node_emb is None or w_first is None:
+            raise ValueError("tsp cache of width 4E needs node_emb and w_first")
+        if tuple(node_emb.shape) != (B_inst, N, EMBED_DIM) or tuple(w_first.shape) != (EMBED_DIM, EMBED_DIM):
+            raise ValueError("node_emb must be [B_inst, N, E] and w_first [E, E]")
+        a.node_emb, a.w_first = _ptr(node_emb, F32, "node_emb"), _ptr(w_first, F32, "w_first")
+    a.cache_width = W
     if forced_actions is not None and tuple(forced_actions.shape) != (B_traj, T_max):
         raise ValueError(f"forced_actions must be [{B_traj}, {T_max}], got {tuple(forced_actions.shape)}")
     if noise is not None and (noise.dim() != 3 or noise.shape[1] != B_traj or noise.shape[2] != N):

@@ -15,6 +15,8 @@ Two execution paths, both CUDA-only:
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -120,7 +122,6 @@ class FusedAttentionModelPolicy(nn.Module):
             raise NotImplementedError(f"decoding kwargs outside the fused path: {list(kw)}")
 
         B, N = td["action_mask"].shape
-        cached = self.decoder._precompute_cache(hidden)
         S, forced_start = 1, False
         if "multistart" in decode_type:
             S = num_starts if num_starts is not None else env.get_num_starts(td)
@@ -130,6 +131,9 @@ class FusedAttentionModelPolicy(nn.Module):
             S = num_samples
         B_traj = B * S
         T_max = N if env_name == "tsp" else 2 * (N - 1)
+        # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
+        # (CO_ROLLOUT_IMPL=v3, the round-1 kernel kept for A/B measurements, needs the table as well)
+        cached = self.decoder._precompute_cache(hidden, first_table=S > 1 or os.environ.get("CO_ROLLOUT_IMPL") == "v3")
 
         forced = None
         if decode_type == "evaluate":
@@ -163,7 +167,9 @@ class FusedAttentionModelPolicy(nn.Module):
                 cached.q_placeholder, cached.w_capacity, td["locs"].contiguous(), demand, vcap, B, N, num_starts=S,
                 forced_start=forced_start, num_loc=num_loc, T_max=T_max, forced_actions=forced,
                 noise=noise.contiguous() if noise is not None else None, tanh_clipping=tanh_clipping,
-                temperature=temperature, seed=seed or 0, offset=philox_offset or 0)
+                temperature=temperature, seed=seed or 0, offset=philox_offset or 0,
+                node_emb=hidden.detach().contiguous() if env_name == "tsp" else None,
+                w_first=cached.w_first.detach() if cached.w_first is not None else None)
         if env_name == "tsp":
             T = N
         elif decode_type == "evaluate":

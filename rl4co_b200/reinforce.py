@@ -204,26 +204,102 @@ def calculate_loss(reward, log_likelihood, bl_val, bl_loss=0):
     return reinforce_loss + bl_loss, reinforce_loss
 
 
-def reinforce_step(policy, env, td, baseline, optimizer=None, decode_type="sampling", seed=None, max_grad_norm=1.0):
+def _bn_modules(module):
+    return [m for m in module.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+
+
+def reinforce_step(policy, env, td, baseline, optimizer=None, decode_type="sampling", seed=None, max_grad_norm=1.0,
+                   micro_batch=None, matmul_precision=None):
     """One REINFORCE training step (reinforce.py:59-111): fused sampling rollout (no grad) ->
-    differentiable log-likelihood of the sampled actions -> loss -> backward -> optimizer."""
+    differentiable log-likelihood of the sampled actions -> loss -> backward -> gradient averaging over ranks
+    -> clip -> optimizer.
+
+    `micro_batch`: batches larger than this are processed in chunks (bounded activation memory: the
+    differentiable pass of 65 536 CVRP-100 instances does not fit one GPU): phase 1 samples every chunk without
+    a graph, the baseline is evaluated once on the WHOLE batch (global mean / all-reduce), phase 2 recomputes
+    each chunk's encoder + log-likelihood with a graph and accumulates its share of the loss gradient.  Train-mode
+    BatchNorm statistics are per chunk (what per-rank statistics are under the reference's DDP); phase 1 freezes
+    the running statistics so that they are updated once per chunk per step.
+    `matmul_precision`: e.g. "medium" = the reference trainer's float32_matmul_precision
+    (rl4co/utils/trainer.py:57,89-90) for the autograd GEMMs; None leaves the global setting alone."""
     policy.train()
-    enc = policy.encoder(td)  # ONE differentiable encoder pass (train-mode norms) shared by both stages
-    with torch.no_grad():
-        out = policy(td, env, phase="train", decode_type=decode_type, encoder_output=(enc[0].detach(), enc[1]),
-                     **({"seed": seed} if seed is not None else {}))
-    ll = evaluate_log_likelihood(policy, td, env, out["actions"], hidden=enc[0])
-    bl_val, bl_loss = baseline.eval(td, out["reward"], env)
-    loss, rl = calculate_loss(out["reward"], ll, bl_val, bl_loss)
-    if optimizer is not None:
-        optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        sync_gradients(policy.parameters())  # DDP-equivalent gradient averaging (no-op on one rank)
-        if max_grad_norm:
-            torch.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)
-        optimizer.step()
-    return {"loss": loss.detach(), "reinforce_loss": rl.detach(), "reward": out["reward"], "log_likelihood": ll.detach(),
-            "bl_val": bl_val, "actions": out["actions"]}
+    prev_prec = None
+    if matmul_precision is not None:
+        prev_prec = torch.get_float32_matmul_precision()
+        torch.set_float32_matmul_precision(matmul_precision)
+    ev0 = ev1 = None
+    try:
+        B = td.batch_size[0]
+        kw = {"seed": seed} if seed is not None else {}
+        if micro_batch is None or B <= micro_batch:
+            enc = policy.encoder(td)  # ONE differentiable encoder pass (train-mode norms) shared by both stages
+            with torch.no_grad():
+                if td["locs"].is_cuda:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                out = policy(td, env, phase="train", decode_type=decode_type, encoder_output=(enc[0].detach(), enc[1]), **kw)
+                if ev1 is not None:
+                    ev1.record()
+            ll = evaluate_log_likelihood(policy, td, env, out["actions"], hidden=enc[0])
+            bl_val, bl_loss = baseline.eval(td, out["reward"], env)
+            loss, rl = calculate_loss(out["reward"], ll, bl_val, bl_loss)
+            reward, actions, chunks = out["reward"], out["actions"], 1
+            if optimizer is not None:
+                optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+        else:
+            spans = [(lo, min(lo + micro_batch, B)) for lo in range(0, B, micro_batch)]
+            chunks = len(spans)
+            bns = _bn_modules(policy)
+            saved = [m.momentum for m in bns]
+            for m in bns:
+                m.momentum = 0.0  # phase 1 must not move the running statistics (phase 2 does, once)
+            outs = []
+            try:
+                with torch.no_grad():
+                    if td["locs"].is_cuda:
+                        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ev0.record()
+                    for i, (lo, hi) in enumerate(spans):
+                        kwi = {"seed": seed * 1_000_003 + i} if seed is not None else {}
+                        outs.append(policy(td[lo:hi], env, phase="train", decode_type=decode_type, **kwi))
+                    if ev1 is not None:
+                        ev1.record()
+            finally:
+                for m, mom in zip(bns, saved):
+                    m.momentum = mom
+            T = max(o["actions"].shape[1] for o in outs)
+            reward = torch.cat([o["reward"] for o in outs])
+            actions = torch.cat([F.pad(o["actions"], (0, T - o["actions"].shape[1])) for o in outs])
+            bl_val, bl_loss = baseline.eval(td, reward, env)
+            if optimizer is not None:
+                optimizer.zero_grad(set_to_none=True)
+            ll_parts, loss = [], torch.zeros((), device=reward.device)
+            for (lo, hi), o in zip(spans, outs):
+                tdc = td[lo:hi]
+                ll_c = evaluate_log_likelihood(policy, tdc, env, o["actions"])
+                bl_c = bl_val[lo:hi] if isinstance(bl_val, torch.Tensor) and bl_val.dim() > 0 and bl_val.shape[0] == B else bl_val
+                part = -((o["reward"] - bl_c) * ll_c).sum() / B   # this chunk's share of the batch mean
+                if optimizer is not None:
+                    part.backward()
+                loss = loss + part.detach()
+                ll_parts.append(ll_c.detach())
+            ll = torch.cat(ll_parts)
+            rl = loss
+            loss = loss + (bl_loss if not isinstance(bl_loss, torch.Tensor) else bl_loss.detach())
+        if optimizer is not None:
+            sync_gradients(policy.parameters())  # DDP-equivalent gradient averaging (no-op on one rank)
+            if max_grad_norm:
+                torch.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)
+            optimizer.step()
+    finally:
+        if prev_prec is not None:
+            torch.set_float32_matmul_precision(prev_prec)
+    res = {"loss": loss.detach(), "reinforce_loss": rl.detach(), "reward": reward, "log_likelihood": ll.detach(),
+           "bl_val": bl_val, "actions": actions, "chunks": chunks}
+    if ev1 is not None:
+        res["rollout_events"] = (ev0, ev1)
+    return res
 
 
 def pomo_step(policy, env, td, num_augment=8, num_starts=None, phase="test", optimizer=None):

@@ -138,3 +138,25 @@ def test_low_temperature_takes_the_stepping_path():
     with torch.no_grad():
         out = pol(td, env, decode_type="sampling", temperature=0.1)
     assert torch.isfinite(out["log_likelihood"]).all()
+
+
+@pytest.mark.parametrize("env_name", ["tsp", "cvrp"])
+def test_reinforce_step_chunked_matches_formula(env_name):
+    """`micro_batch`: sampling per chunk, ONE baseline over the whole batch, per-chunk differentiable pass with
+    gradient accumulation; the reported loss is the batch-mean REINFORCE loss of the sampled trajectories."""
+    from rl4co_b200.reinforce import get_reinforce_baseline, reinforce_step
+
+    env, pol, td = _setup(env_name, 20, 80, layers=1)
+    bl = get_reinforce_baseline("mean")
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-3)
+    before = [p.detach().clone() for p in pol.parameters()]
+    res = reinforce_step(pol, env, td, bl, opt, seed=4, micro_batch=32, matmul_precision="highest")
+    assert res["chunks"] == 3 and res["reward"].shape == (80,) and res["actions"].shape[0] == 80
+    assert abs(float(res["bl_val"]) - res["reward"].mean().item()) < 1e-5  # baseline over the WHOLE batch
+    ref = O.reinforce_loss(res["reward"].cpu(), res["log_likelihood"].cpu(), torch.as_tensor(float(res["bl_val"])))
+    torch.testing.assert_close(res["reinforce_loss"].cpu(), ref, rtol=1e-4, atol=1e-6)
+    changed = sum((a != b.detach()).any().item() for a, b in zip(before, pol.parameters()))
+    assert changed > 5
+    # running BatchNorm statistics moved once per chunk (phase 1 is frozen): num_batches_tracked == chunks
+    nbt = [m.num_batches_tracked.item() for m in pol.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    assert nbt and all(v == 3 for v in nbt)
