@@ -215,6 +215,26 @@ int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo, float* C,
                    const float* shift, int M, int Nout, int K, int lda, int ldc, int ldr,
                    int relu, void* stream);
 
+/* Encoder feed-forward block in ONE kernel (the [M, 512] hidden activation never leaves the SM):
+ *   out = ((x + relu(x W1^T + b1) W2^T + b2)) * scale + shift,  x [M,128], W1 [512,128], W2 [128,512]
+ * = SkipConnection(MLP) + eval-mode BatchNorm of MultiHeadAttentionLayer (rl4co/models/nn/graph/attnnet.py:
+ * 33-53, nn/mlp.py:45-60, nn/ops.py:9-15,30-46).  Weights pre-split with co_split_tf32; scale / shift NULL
+ * (both) for no affine; ldx / ldo row strides in floats (% 4 == 0); 16-byte aligned pointers. */
+int co_ffn_fused(const float* x, const float* w1hi, const float* w1lo, const float* b1, const float* w2hi,
+                 const float* w2lo, const float* b2, const float* scale, const float* shift, float* out,
+                 int M, int ldx, int ldo, void* stream);
+
+/* ------------------------------------------------------------------ data path
+ * On-device instance generation (Philox4x32-10 keyed by seed / offset; same seed -> same data on every GPU) and
+ * the dihedral-8 augmentation as streaming kernels.
+ *   co_generate_uniform: out[i] = U[0,1) * (hi - lo) + lo           (envs/common/utils.py:61-62 "uniform")
+ *   co_generate_demand : out[i] = (int(U * (max-min) + (min-1)) + 1) / capacity   (cvrp/generator.py:126-137)
+ *   co_dihedral8       : out[a*B + b] = a-th image of locs[b], a = 0..7            (data/transforms.py:16-38) */
+int co_generate_uniform(float* out, long n, uint64_t seed, uint64_t offset, float lo, float hi, void* stream);
+int co_generate_demand(float* out, long n, uint64_t seed, uint64_t offset, int min_demand, int max_demand,
+                       float capacity, void* stream);
+int co_dihedral8(const float* locs, float* out, long B, int N, void* stream);
+
 /* Encoder self-attention core: F.scaled_dot_product_attention of MultiHeadAttention
  * (rl4co/models/nn/attention.py:110-134) on the packed projection qkv [B*N, 3E] ("three h d"),
  * 8 heads x 16, no mask, fp32 -> out [B*N, E] ("h d"); N <= 128. */

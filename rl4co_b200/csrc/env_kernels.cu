@@ -12,6 +12,53 @@ namespace co {
 
 constexpr int ROWS_PER_CTA = 8;  // 8 warps / CTA, one row each
 
+// Copy one row of 0/1 bytes (bool mask / uint8 visited) with byte `set_idx` forced to `set_val`, 16 bytes per
+// lane wherever the row allows it.  Rows start at arbitrary byte offsets (row * N), so the row is cut at the
+// 16-byte boundaries of the address space: head and tail pieces move byte-wise, every interior word is one
+// LDG.128 + one STG.128 (N = 100: 5-6 vector words + <= 30 bytes instead of 100 byte loads + 100 byte stores).
+// Returns this lane's count of non-zero output bytes (values are 0 / 1).
+__device__ __forceinline__ int copy_row_set_byte(const uint8_t* in, uint8_t* out, int N, int set_idx, uint8_t set_val,
+                                                 int lane) {
+  const uintptr_t ai = reinterpret_cast<uintptr_t>(in), ao = reinterpret_cast<uintptr_t>(out);
+  int count = 0;
+  if (((ai ^ ao) & 15) != 0 || N < 48) {  // different misalignment of source and destination, or a short row
+    for (int n = lane; n < N; n += 32) {
+      const uint8_t v = (n == set_idx) ? set_val : in[n];
+      out[n] = v;
+      count += v;
+    }
+    return count;
+  }
+  const int head = (int)((16 - (ai & 15)) & 15);          // bytes before the first aligned word
+  const int words = (N - head) >> 4;                      // whole 16-byte words inside the row
+  const int tail0 = head + (words << 4);                  // first byte after the last whole word
+  for (int n = lane; n < head; n += 32) {
+    const uint8_t v = (n == set_idx) ? set_val : in[n];
+    out[n] = v;
+    count += v;
+  }
+  for (int n = tail0 + lane; n < N; n += 32) {
+    const uint8_t v = (n == set_idx) ? set_val : in[n];
+    out[n] = v;
+    count += v;
+  }
+  const uint4* iw = reinterpret_cast<const uint4*>(in + head);
+  uint4* ow = reinterpret_cast<uint4*>(out + head);
+  for (int w = lane; w < words; w += 32) {
+    uint4 v = iw[w];
+    const int rel = set_idx - (head + (w << 4));          // position of the forced byte inside this word
+    if (rel >= 0 && rel < 16) {
+      uint32_t* c = reinterpret_cast<uint32_t*>(&v);
+      const int sh = 8 * (rel & 3);
+      c[rel >> 2] = (c[rel >> 2] & ~(0xffu << sh)) | ((uint32_t)set_val << sh);
+    }
+    ow[w] = v;
+    count += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) +
+             __popc(v.w & 0x01010101u);
+  }
+  return count;
+}
+
 __global__ void __launch_bounds__(256) tsp_step_kernel(const int64_t* __restrict__ action,
                                                         const uint8_t* mask_in, uint8_t* mask_out,
                                                         int64_t* first_node, int64_t* current_node,
@@ -20,14 +67,8 @@ __global__ void __launch_bounds__(256) tsp_step_kernel(const int64_t* __restrict
   int lane = threadIdx.x & 31;
   if (row >= B) return;
   int a = (int)action[row];
-  const uint8_t* mi = mask_in + (size_t)row * N;
-  uint8_t* mo = mask_out + (size_t)row * N;
-  int left = 0;
-  for (int n = lane; n < N; n += 32) {
-    uint8_t v = (n == a) ? (uint8_t)0 : mi[n];
-    mo[n] = v;
-    left += v ? 1 : 0;
-  }
+  // action_mask.scatter(-1, action, 0) as a row copy with one byte cleared (16-byte words where possible)
+  int left = copy_row_set_byte(mask_in + (size_t)row * N, mask_out + (size_t)row * N, N, a, 0, lane);
   left = __reduce_add_sync(FULL, left);
   if (lane == 0) {
     done[row] = (left == 0);
@@ -85,12 +126,8 @@ __global__ void __launch_bounds__(256) cvrp_step_kernel(const int64_t* __restric
   float used = (used_in[row] + dem[didx]) * (a != 0 ? 1.0f : 0.0f);
   const uint8_t* vi = visited_in + (size_t)row * N;
   uint8_t* vo = visited_out + (size_t)row * N;
-  int cnt = 0;
-  for (int n = lane; n < N; n += 32) {
-    uint8_t v = (n == a) ? (uint8_t)1 : vi[n];
-    vo[n] = v;
-    cnt += v;  // visited.sum(-1): sums the uint8 values
-  }
+  // visited.scatter(-1, action, 1) and visited.sum(-1) (sums the uint8 values, which are 0 / 1)
+  int cnt = copy_row_set_byte(vi, vo, N, a, 1, lane);
   cnt = __reduce_add_sync(FULL, cnt);
   __syncwarp();
   if (lane == 0) {
@@ -114,13 +151,22 @@ __global__ void __launch_bounds__(256) tour_length_kernel(const float2* __restri
   // ordered tour: [depot?] a_0 .. a_{T-1}; edge k joins tour[k] and tour[(k+1) % L]
   const int L = T + (with_depot ? 1 : 0);
   float acc = 0.f;
-  for (int k = lane; k < L; k += 32) {
-    int k1 = (k + 1 == L) ? 0 : k + 1;
-    int n0 = with_depot ? (k == 0 ? 0 : (int)a[k - 1]) : (int)a[k];
-    int n1 = with_depot ? (k1 == 0 ? 0 : (int)a[k1 - 1]) : (int)a[k1];
-    float2 p0 = x[n0], p1 = x[n1];
-    float dx = p1.x - p0.x, dy = p1.y - p0.y;
-    acc += sqrtf(dx * dx + dy * dy);
+  // every action is read from HBM once: lane l holds tour[k] for k = base + l; its successor comes from lane l + 1
+  // (the chunk's last lane reads one element ahead), so each 32-edge chunk costs one coalesced 256-byte load
+  for (int base = 0; base < L; base += 32) {
+    const int k = base + lane;
+    int n0 = 0;
+    if (k < L) n0 = with_depot ? (k == 0 ? 0 : (int)a[k - 1]) : (int)a[k];
+    int n1 = __shfl_down_sync(FULL, n0, 1);
+    if (lane == 31 || k + 1 >= L) {
+      const int k1 = (k + 1 >= L) ? 0 : k + 1;
+      n1 = with_depot ? (k1 == 0 ? 0 : (int)a[k1 - 1]) : (int)a[k1];
+    }
+    if (k < L) {
+      const float2 p0 = x[n0], p1 = x[n1];
+      const float dx = p1.x - p0.x, dy = p1.y - p0.y;
+      acc += sqrtf(dx * dx + dy * dy);
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) reward[row] = -acc;

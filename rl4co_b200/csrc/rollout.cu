@@ -5,10 +5,8 @@
 #include "co_common.cuh"
 
 namespace co {
-int rollout_tsp(const co_rollout_args& A, cudaStream_t st);       // head-wise kernel (rollout_hw_impl.cuh)
+int rollout_tsp(const co_rollout_args& A, cudaStream_t st);
 int rollout_cvrp(const co_rollout_args& A, cudaStream_t st);
-int rollout_v3_tsp(const co_rollout_args& A, cudaStream_t st);    // round-1 kernel (rollout_impl.cuh), CO_ROLLOUT_IMPL=v3
-int rollout_v3_cvrp(const co_rollout_args& A, cudaStream_t st);
 int rollout_ms_tsp(const co_rollout_args& A, cudaStream_t st);   // query-batched (num_starts > 1)
 int rollout_ms_cvrp(const co_rollout_args& A, cudaStream_t st);
 }  // namespace co
@@ -41,9 +39,6 @@ extern "C" int co_rollout(const co_rollout_args* args, void* stream) {
   // S > 1 trajectories per instance: the query-batched kernel advances 4 of them per pass
   static const bool use_ms = !(getenv("CO_ROLLOUT_MS") && atoi(getenv("CO_ROLLOUT_MS")) == 0);
   const bool ms = use_ms && A.num_starts > 1;
-  // CO_ROLLOUT_IMPL=v3 selects the round-1 single-trajectory kernel (A/B measurements); read per call
-  const char* impl = getenv("CO_ROLLOUT_IMPL");
-  const bool v3 = impl && !strcmp(impl, "v3");
   if (A.cache_width == 0) A.cache_width = co_cache_width(A.env_kind);
   if (A.env_kind == CO_ENV_TSP) {
     if (!A.q_placeholder) return fail(CO_ERR_BAD_ARG, "co_rollout: q_placeholder required for tsp%s");
@@ -51,14 +46,14 @@ extern "C" int co_rollout(const co_rollout_args* args, void* stream) {
     if (A.cache_width != 4 * E && A.cache_width != 5 * E) return fail(CO_ERR_BAD_ARG, "co_rollout: tsp cache_width must be 4E or 5E%s");
     if (A.cache_width == 4 * E && (!A.node_emb || !A.w_first))
       return fail(CO_ERR_BAD_ARG, "co_rollout: tsp cache_width 4E needs node_emb and w_first%s");
-    if ((ms || v3) && A.cache_width != 5 * E)
-      return fail(CO_ERR_UNSUPPORTED, "co_rollout: this kernel variant needs the 5E tsp cache (first-node table)%s");
-    return ms ? rollout_ms_tsp(A, st) : (v3 ? rollout_v3_tsp(A, st) : rollout_tsp(A, st));
+    if (ms && A.cache_width != 5 * E)
+      return fail(CO_ERR_UNSUPPORTED, "co_rollout: the multistart kernel needs the 5E tsp cache (first-node table)%s");
+    return ms ? rollout_ms_tsp(A, st) : rollout_tsp(A, st);
   }
   if (A.env_kind == CO_ENV_CVRP) {
     if (!A.demand || !A.w_capacity) return fail(CO_ERR_BAD_ARG, "co_rollout: demand / w_capacity required for cvrp%s");
     if (A.cache_width != 4 * E) return fail(CO_ERR_BAD_ARG, "co_rollout: cvrp cache_width must be 4E%s");
-    return ms ? rollout_ms_cvrp(A, st) : (v3 ? rollout_v3_cvrp(A, st) : rollout_cvrp(A, st));
+    return ms ? rollout_ms_cvrp(A, st) : rollout_cvrp(A, st);
   }
   return fail(CO_ERR_BAD_ARG, "co_rollout: unknown env kind%s");
 }

@@ -28,6 +28,11 @@
 //     over demand ranks (ffs = unvisited customer of least demand) instead of a block-wide OR;
 //   * exactly two block barriers per node selection; no state in HBM.
 // HBM traffic per instance = one read of its cache rows + T*(8+4) B of outputs.
+//
+// Cache layouts (args.cache_width): 4E = [K | V | L' | cur-table] (default): the TSP first-node half of the context
+// projection is NOT a per-node table (only one row per episode was ever read) but one 128x128 GEMV per episode from
+// node_emb / w_first;  5E (tsp) = [K | V | L' | first-table | cur-table], still accepted (the multistart kernel reads
+// one table row per start).
 #pragma once
 #include "co_common.cuh"
 
@@ -54,6 +59,7 @@ struct Smem {
   float ptab[(32 * SPL + 1) * E];   // current-node context table; last row = zeros
   float qfix[E];                    // per-episode fixed part of the query
   float wcap[E];                    // cvrp: remaining-capacity column of project_context
+  float hfirst[E];                  // tsp, 4E cache: embedding of the first node (GEMV operand; 16-byte aligned)
   float o[8 * (16 * SPL + 4) + 8];  // concatenated heads (padded per part)
   float tile[8][32 * TILE_LD];      // per-warp transpose tile for the value reduction
   unsigned red_key[8];              // per-warp best key (order-preserving uint of a float)
@@ -86,6 +92,25 @@ __device__ __forceinline__ float funkey(unsigned k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
+// tsp, 4E cache: qfix[e] += sum_c w_first[e][c] * hfirst[c]  (project_context[:, :E] @ h[first], context.py:129-133).
+// Once per episode; kept out of line so that its address arithmetic does not cost the episode loop registers.
+// 256 threads: two per output channel, 64 input channels each.
+static __device__ __noinline__ void first_node_gemv(const float* __restrict__ w_first, const float* hfirst, float* qfix, int tid) {
+  const int e = tid >> 1, half = tid & 1;
+  const float4* wr = reinterpret_cast<const float4*>(w_first + (size_t)e * E + 64 * half);
+  const float4* hv = reinterpret_cast<const float4*>(hfirst + 64 * half);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    const float4 w0 = __ldg(wr + c), x0 = hv[c], w1 = __ldg(wr + c + 1), x1 = hv[c + 1];
+    s0 = fmaf(w0.x, x0.x, s0); s0 = fmaf(w0.y, x0.y, s0); s0 = fmaf(w0.z, x0.z, s0); s0 = fmaf(w0.w, x0.w, s0);
+    s1 = fmaf(w1.x, x1.x, s1); s1 = fmaf(w1.y, x1.y, s1); s1 = fmaf(w1.z, x1.z, s1); s1 = fmaf(w1.w, x1.w, s1);
+  }
+  float sacc = s0 + s1;
+  sacc += __shfl_xor_sync(FULL, sacc, 1);
+  if (half == 0) qfix[e] += sacc;
+}
+
 template <int ENV>
 __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used, float thr, int cur, bool anyfeas) {
   if (ENV == CO_ENV_TSP) return !visbit;
@@ -94,12 +119,13 @@ __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used
   return !visbit && !((d + used) > thr);
 }
 
-template <int SPL, int ENV, int MODE>
+template <int SPL, int ENV, int MODE, int CWB>  // CWB = cache blocks of E floats per node row: 4, or 5 (tsp first-node table)
 __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_rollout_args A) {
   using C = Cfg<SPL>;
   constexpr int NS = C::NS, PARTS = C::PARTS, NPW = C::NPW, EPP = C::EPP, OPAD = C::OPAD;
-  constexpr int CW = (ENV == CO_ENV_TSP ? 5 : 4) * E;   // cache row width
-  constexpr int CUR_BLK = (ENV == CO_ENV_TSP ? 4 : 3);  // block holding the current-node table
+  constexpr int CW = CWB * E;        // cache row width: 4E, or 5E (tsp with the first-node table)
+  constexpr int CUR_BLK = CWB - 1;   // block holding the current-node table (always the last one)
+  constexpr bool first_table = (ENV == CO_ENV_TSP) && (CWB == 5);
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<SPL>& sm = *reinterpret_cast<Smem<SPL>*>(smem_raw);
@@ -202,10 +228,25 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 #pragma unroll
       for (int k = 0; k < SPL; ++k) out[k] = a2[k].x + a2[k].y;
     };
+    // tsp: qfix += project_context[:, :E] @ h[first] (context.py:129-133); callers barrier before and after
+    auto add_first = [&](int a_first) {
+      if (first_table) {
+        if (tid < E) sm.qfix[tid] += __ldg(crow + (size_t)a_first * CW + 3 * E + tid);
+      } else {
+        if (tid < E) sm.hfirst[tid] = __ldg(A.node_emb + ((size_t)b * N + a_first) * E + tid);
+        __syncthreads();
+        first_node_gemv(A.w_first, sm.hfirst, sm.qfix, tid);
+      }
+    };
     float WK[SPL], FK[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) { WK[k] = 0.f; FK[k] = 0.f; }
     if (ENV == CO_ENV_CVRP) head_dot(sm.wcap, WK);
+    if (b + (int)gridDim.x < B_inst) {  // next instance's cache rows -> L2 while this episode runs
+      const char* nxt = reinterpret_cast<const char*>(A.cache + (size_t)(b + gridDim.x) * N * CW);
+      const int lines = (N * CW * 4 + 127) >> 7;
+      for (int i = tid; i < lines; i += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)i << 7)));
+    }
 
     for (int s = 0; s < S; ++s) {
       const int traj = s * B_inst + b;  // start-major, rl4co/utils/ops.py:10-29
@@ -278,7 +319,10 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         const int a0 = (s % A.num_loc) + (ENV == CO_ENV_CVRP ? 1 : 0);
         if (tid == 0) { act_row[0] = a0; lp_row[0] = 0.f; }
         env_step(a0);
-        if (ENV == CO_ENV_TSP && tid < E) sm.qfix[tid] += __ldg(crow + (size_t)a0 * CW + 3 * E + tid);
+        if (ENV == CO_ENV_TSP) {
+          __syncthreads();  // qfix initialised
+          add_first(a0);
+        }
       } else if (ENV == CO_ENV_CVRP) {
         anyfeas = !((sm.dem[sm.order[0]] + used) > thr);
       }
@@ -423,8 +467,9 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         env_step(a);
         ++dstep;
         if (was_first) {  // context from now on: [h_first ; h_cur], context.py:129-133
-          if (tid < E) sm.qfix[tid] = (A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f) +
-                                      __ldg(crow + (size_t)a * CW + 3 * E + tid);
+          if (tid < E) sm.qfix[tid] = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;
+          __syncthreads();
+          add_first(a);
           __syncthreads();
           head_dot(sm.qfix, FK);
         }
@@ -447,9 +492,9 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
   }
 }
 
-template <int SPL, int ENV, int MODE>
+template <int SPL, int ENV, int MODE, int CWB>
 static int launch(const co_rollout_args& A, cudaStream_t st) {
-  auto kern = rollout_kernel<SPL, ENV, MODE>;
+  auto kern = rollout_kernel<SPL, ENV, MODE, CWB>;
   const size_t smem = sizeof(Smem<SPL>);
   static PerDeviceOnce once;
   static int ctas_per_sm = 1;
@@ -472,10 +517,15 @@ static int dispatch(const co_rollout_args& A, cudaStream_t st) {
   const int spl = A.N <= 32 ? 1 : (A.N <= 64 ? 2 : 4);
   const int mode = A.select_mode == CO_SELECT_GREEDY ? CO_MODE_GREEDY
                    : (A.select_mode == CO_SELECT_EVALUATE ? CO_MODE_EVALUATE : CO_MODE_SAMPLE);
-#define CO_CASE(S_, M_) if (spl == S_ && mode == M_) return launch<S_, ENV, M_>(A, st)
-  CO_CASE(1, CO_MODE_GREEDY); CO_CASE(2, CO_MODE_GREEDY); CO_CASE(4, CO_MODE_GREEDY);
-  CO_CASE(1, CO_MODE_SAMPLE); CO_CASE(2, CO_MODE_SAMPLE); CO_CASE(4, CO_MODE_SAMPLE);
-  CO_CASE(1, CO_MODE_EVALUATE); CO_CASE(2, CO_MODE_EVALUATE); CO_CASE(4, CO_MODE_EVALUATE);
+  const int cwb = A.cache_width / E;
+#define CO_CASE(S_, M_)                                                                      \
+  if (spl == S_ && mode == M_) {                                                             \
+    if (cwb == 4) return launch<S_, ENV, M_, 4>(A, st);                                      \
+    if (ENV == CO_ENV_TSP && cwb == 5) return launch<S_, ENV, M_, (ENV == CO_ENV_TSP ? 5 : 4)>(A, st); \
+  }
+  CO_CASE(1, CO_MODE_GREEDY) CO_CASE(2, CO_MODE_GREEDY) CO_CASE(4, CO_MODE_GREEDY)
+  CO_CASE(1, CO_MODE_SAMPLE) CO_CASE(2, CO_MODE_SAMPLE) CO_CASE(4, CO_MODE_SAMPLE)
+  CO_CASE(1, CO_MODE_EVALUATE) CO_CASE(2, CO_MODE_EVALUATE) CO_CASE(4, CO_MODE_EVALUATE)
 #undef CO_CASE
   return fail(CO_ERR_BAD_ARG, "co_rollout: no kernel variant%s");
 }

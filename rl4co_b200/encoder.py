@@ -186,6 +186,15 @@ class AttentionModelEncoder(nn.Module):
         return acc
 
     @staticmethod
+    def _ffn_fusable(ffn):
+        import os
+
+        lins = ffn.lins
+        return (os.environ.get("CO_FFN", "fused") != "split" and len(lins) == 2 and lins[0].bias is not None
+                and lins[1].bias is not None and tuple(lins[0].weight.shape) == (512, 128)
+                and tuple(lins[1].weight.shape) == (128, 512) and type(ffn) is MLP)  # MLP: ReLU between the two Linear
+
+    @staticmethod
     def _bn_affine(norm):
         bn = norm.normalizer
         if not isinstance(bn, nn.BatchNorm1d):
@@ -217,10 +226,19 @@ class AttentionModelEncoder(nn.Module):
                 h = native.gemm_tf32x3(att, *self._split(mha.out_proj.weight), bias=mha.out_proj.bias, residual=h)
                 h = norm1(h.view(B, N, E)).reshape(B * N, E).contiguous()
             lins = ffn.lins
+            aff = self._bn_affine(norm2)
+            if self._ffn_fusable(ffn):
+                # FF1 -> ReLU -> FF2 (+ skip, + folded BatchNorm) in one kernel: the [B*N, 512] hidden activation
+                # stays in tensor memory (co_ffn_fused); CO_FFN=split forces the separate GEMMs
+                w1, w2 = self._split(lins[0].weight), self._split(lins[1].weight)
+                h = native.ffn_fused(h, w1[0], w1[1], lins[0].bias, w2[0], w2[1], lins[1].bias,
+                                     scale=aff[0] if aff is not None else None, shift=aff[1] if aff is not None else None)
+                if aff is None:
+                    h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()
+                continue
             f = h
             for lin in lins[:-1]:
                 f = native.gemm_tf32x3(f, *self._split(lin.weight), bias=lin.bias, relu=True)
-            aff = self._bn_affine(norm2)
             last = lins[-1]
             if last.weight.shape[1] % 128 == 0 and last.weight.shape[1] > 128:
                 h = self._linear_splitk(f, last, h, aff)

@@ -34,23 +34,51 @@ class Generator:
         return self._generate(batch_size)
 
 
-class TSPGenerator(Generator):
+class _DeviceStream:
+    """On-device generation state: `device="cuda"` makes a generator write instances straight into HBM with
+    co_generate_uniform / co_generate_demand (Philox keyed by `seed`; every call advances `offset`, so successive
+    batches differ and a (seed, call index) pair always reproduces the same batch).  Default: torch's CPU
+    generator in the reference's call order (bit-identical to the reference under the same torch seed)."""
+
+    def _init_stream(self, device, seed):
+        self.device = None if device is None else torch.device(device)
+        self.seed = 0 if seed is None else int(seed)
+        self.calls = 0
+
+    @property
+    def on_device(self):
+        return self.device is not None and self.device.type == "cuda"
+
+    def _next_offset(self, streams: int) -> int:
+        off = self.calls * streams
+        self.calls += 1
+        return off
+
+
+class TSPGenerator(Generator, _DeviceStream):
     """rl4co/envs/routing/tsp/generator.py:14-58 (uniform locations)."""
 
-    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, **_):
+    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, device=None, seed=None, **_):
         self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
+        self._init_stream(device, seed)
 
     def _generate(self, batch_size) -> TensorDict:
+        if self.on_device:
+            locs = native.generate_uniform((*batch_size, self.num_loc, 2), self.device, self.seed, self._next_offset(1),
+                                           self.min_loc, self.max_loc)
+            return TensorDict({"locs": locs}, batch_size=batch_size, device=self.device)
         locs = torch.rand(*batch_size, self.num_loc, 2) * (self.max_loc - self.min_loc) + self.min_loc
         return TensorDict({"locs": locs}, batch_size=batch_size)
 
 
-class CVRPGenerator(Generator):
+class CVRPGenerator(Generator, _DeviceStream):
     """rl4co/envs/routing/cvrp/generator.py:33-140 (uniform locations, integer demands 1..9
     over the Kool et al. capacity table, depot = first sampled point)."""
 
     def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, min_demand: int = 1,
-                 max_demand: int = 10, vehicle_capacity: float = 1.0, capacity: float | None = None, **_):
+                 max_demand: int = 10, vehicle_capacity: float = 1.0, capacity: float | None = None, device=None,
+                 seed=None, **_):
+        self._init_stream(device, seed)
         self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
         self.min_demand, self.max_demand = min_demand, max_demand
         self.vehicle_capacity = vehicle_capacity
@@ -61,6 +89,16 @@ class CVRPGenerator(Generator):
         self.capacity = capacity
 
     def _generate(self, batch_size) -> TensorDict:
+        if self.on_device:
+            off = self._next_offset(2)
+            locs = native.generate_uniform((*batch_size, self.num_loc + 1, 2), self.device, self.seed, off,
+                                           self.min_loc, self.max_loc)
+            demand = native.generate_demand((*batch_size, self.num_loc), self.device, self.seed, off + 1,
+                                            self.min_demand, self.max_demand, self.capacity)
+            return TensorDict(
+                {"locs": locs[..., 1:, :], "depot": locs[..., 0, :], "demand": demand,
+                 "capacity": torch.full((*batch_size, 1), self.capacity, device=self.device)},
+                batch_size=batch_size, device=self.device)
         locs = torch.rand(*batch_size, self.num_loc + 1, 2) * (self.max_loc - self.min_loc) + self.min_loc
         lo, hi = self.min_demand - 1, self.max_demand - 1
         demand = torch.rand(*batch_size, self.num_loc) * (hi - lo) + lo

@@ -21,8 +21,9 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
 SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "gemm_tf32x3.cu",
-           "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu"]
-HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_hw_impl.cuh", "rollout_ms_impl.cuh"]
+           "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
+           "ffn_fused.cu", "data_kernels.cu"]
+HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
@@ -35,6 +36,7 @@ EXPORTS = [
     "co_version", "co_last_error_string", "co_device_sm_count", "co_tsp_step", "co_cvrp_action_mask",
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
+    "co_ffn_fused", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
 ]
 
 
@@ -129,6 +131,10 @@ def lib() -> ctypes.CDLL:
     L.co_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]
     L.co_gemm_tf32x3.argtypes = [c_void_p] * 8 + [c_int] * 7 + [c_void_p]
     L.co_encoder_mha.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    L.co_ffn_fused.argtypes = [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]
+    L.co_generate_uniform.argtypes = [c_void_p, ctypes.c_long, c_uint64, c_uint64, c_float, c_float, c_void_p]
+    L.co_generate_demand.argtypes = [c_void_p, ctypes.c_long, c_uint64, c_uint64, c_int, c_int, c_float, c_void_p]
+    L.co_dihedral8.argtypes = [c_void_p, c_void_p, ctypes.c_long, c_int, c_void_p]
     _lib = L
     return L
 
@@ -325,6 +331,51 @@ def encoder_mha(qkv, B, N):
     """Self-attention core on the packed [B*N, 384] projection -> [B*N, 128]."""
     out = torch.empty(B * N, EMBED_DIM, dtype=F32, device=qkv.device)
     _check(lib().co_encoder_mha(_ptr(qkv, F32, "qkv"), _ptr(out, F32, "out"), B, N, _stream()), "co_encoder_mha")
+    return out
+
+
+@_on_device_of_first_tensor
+def ffn_fused(x, w1_hi, w1_lo, b1, w2_hi, w2_lo, b2, scale=None, shift=None, out=None):
+    """out = ((x + relu(x W1^T + b1) W2^T + b2)) * scale + shift in one kernel (co_ffn_fused); x [M, 128] with
+    row stride % 4 == 0, W1 [512, 128], W2 [128, 512] pre-split by `split_tf32`."""
+    M = x.shape[0]
+    if x.dim() != 2 or x.shape[1] != EMBED_DIM or x.stride(1) != 1:
+        raise ValueError(f"x must be [M, {EMBED_DIM}] with unit inner stride, got {tuple(x.shape)}")
+    if tuple(w1_hi.shape) != (4 * EMBED_DIM, EMBED_DIM) or tuple(w2_hi.shape) != (EMBED_DIM, 4 * EMBED_DIM):
+        raise ValueError("co_ffn_fused is instantiated for a 128 -> 512 -> 128 feed-forward block")
+    if out is None:
+        out = torch.empty(M, EMBED_DIM, dtype=F32, device=x.device)
+    _check(lib().co_ffn_fused(_ptr(x, F32, "x", True), _ptr(w1_hi, F32, "w1_hi"), _ptr(w1_lo, F32, "w1_lo"),
+                              _ptr(b1, F32, "b1"), _ptr(w2_hi, F32, "w2_hi"), _ptr(w2_lo, F32, "w2_lo"),
+                              _ptr(b2, F32, "b2"), _ptr(scale, F32, "scale"), _ptr(shift, F32, "shift"),
+                              _ptr(out, F32, "out", True), M, x.stride(0), out.stride(0), _stream()), "co_ffn_fused")
+    return out
+
+
+def generate_uniform(shape, device, seed: int, offset: int = 0, lo: float = 0.0, hi: float = 1.0):
+    """U[lo, hi) floats generated on the device (Philox keyed by seed / offset)."""
+    out = torch.empty(shape, dtype=F32, device=device)
+    with torch.cuda.device(out.device):
+        _check(lib().co_generate_uniform(_ptr(out, F32, "out"), out.numel(), int(seed), int(offset), float(lo), float(hi),
+                                         _stream()), "co_generate_uniform")
+    return out
+
+
+def generate_demand(shape, device, seed: int, offset: int, min_demand: int, max_demand: int, capacity: float):
+    """CVRP demands (int(U * (max-min) + (min-1)) + 1) / capacity generated on the device."""
+    out = torch.empty(shape, dtype=F32, device=device)
+    with torch.cuda.device(out.device):
+        _check(lib().co_generate_demand(_ptr(out, F32, "out"), out.numel(), int(seed), int(offset), int(min_demand),
+                                        int(max_demand), float(capacity), _stream()), "co_generate_demand")
+    return out
+
+
+@_on_device_of_first_tensor
+def dihedral8(locs):
+    """[B, N, 2] -> [8B, N, 2] (aug-major), one kernel."""
+    B, N, _ = locs.shape
+    out = torch.empty(8 * B, N, 2, dtype=F32, device=locs.device)
+    _check(lib().co_dihedral8(_ptr(locs, F32, "locs"), _ptr(out, F32, "out"), B, N, _stream()), "co_dihedral8")
     return out
 
 

@@ -97,5 +97,11 @@ class StateAugmentation:
         td_aug = batchify(td, self.num_augment)
         for feat in self.feats:
             x = td_aug[feat]
-            td_aug.set(feat, dihedral_8_augmentation(x[: x.shape[0] // 8]))
+            base = x[: x.shape[0] // 8]
+            if base.is_cuda and base.dim() == 3 and base.shape[-1] == 2 and base.dtype == torch.float32:
+                from . import native
+
+                td_aug.set(feat, native.dihedral8(base.contiguous()))  # one kernel: 8 B read, 64 B written per node
+            else:
+                td_aug.set(feat, dihedral_8_augmentation(base))
         return td_aug

@@ -132,8 +132,7 @@ class FusedAttentionModelPolicy(nn.Module):
         B_traj = B * S
         T_max = N if env_name == "tsp" else 2 * (N - 1)
         # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
-        # (CO_ROLLOUT_IMPL=v3, the round-1 kernel kept for A/B measurements, needs the table as well)
-        cached = self.decoder._precompute_cache(hidden, first_table=S > 1 or os.environ.get("CO_ROLLOUT_IMPL") == "v3")
+        cached = self.decoder._precompute_cache(hidden, first_table=S > 1)
 
         forced = None
         if decode_type == "evaluate":

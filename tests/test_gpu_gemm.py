@@ -67,3 +67,47 @@ def test_gemm_strided_views_and_column_block_output():
     ref = a.double() @ w.double().t()
     torch.testing.assert_close(outbuf[:, 128:384].double(), ref, rtol=1e-5, atol=1e-5)
     assert (outbuf[:, :128] == 0).all() and (outbuf[:, 384:] == 0).all()
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 129, 1000, 148 * 128 + 77, 40000])
+@pytest.mark.parametrize("affine", [True, False])
+def test_ffn_fused_vs_float64(M, affine):
+    """co_ffn_fused (FF1 -> ReLU -> FF2 + skip + folded BatchNorm, hidden activation in tensor memory) against a
+    float64 evaluation of SkipConnection(MLP) + eval BatchNorm (nn/graph/attnnet.py:33-53).  M = 40 000 makes the
+    persistent CTAs loop over several tiles (weight ring / accumulator phase wrap-around)."""
+    from rl4co_b200 import native
+
+    torch.manual_seed(M)
+    dev = "cuda:0"
+    x = torch.randn(M, 128, device=dev) * 1.3
+    w1 = torch.randn(512, 128, device=dev) / 128 ** 0.5
+    b1 = torch.randn(512, device=dev) * 0.1
+    w2 = torch.randn(128, 512, device=dev) / 512 ** 0.5
+    b2 = torch.randn(128, device=dev) * 0.1
+    scale = (1 + 0.2 * torch.randn(128, device=dev)) if affine else None
+    shift = (0.1 * torch.randn(128, device=dev)) if affine else None
+    w1s, w2s = native.split_tf32(w1), native.split_tf32(w2)
+    out = native.ffn_fused(x, w1s[0], w1s[1], b1, w2s[0], w2s[1], b2, scale, shift)
+    xd = x.double()
+    ref = xd + torch.relu(xd @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+    if affine:
+        ref = ref * scale.double() + shift.double()
+    torch.testing.assert_close(out.double(), ref, rtol=2e-5, atol=2e-5)
+
+
+def test_encoder_fused_ffn_equals_split_path(monkeypatch):
+    """The encoder with co_ffn_fused (default) and with the separate GEMMs (CO_FFN=split) agree to fp32 round-off."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(0)
+    dev = "cuda:0"
+    env = get_env("tsp", generator_params=dict(num_loc=100))
+    pol = FusedAttentionModelPolicy(env_name="tsp", num_encoder_layers=3).to(dev).eval()
+    td = env.reset(env.generator(300).to(dev))
+    with torch.inference_mode():
+        monkeypatch.setenv("CO_FFN", "split")
+        h_split, _ = pol.encoder(td)
+        monkeypatch.delenv("CO_FFN")
+        h_fused, _ = pol.encoder(td)
+    torch.testing.assert_close(h_fused, h_split, rtol=2e-5, atol=2e-5)

@@ -293,7 +293,10 @@ def test_rollout_multistart_vs_golden(golden, dev, name, graph_ctx, gemm):
     same = _rows_equal(out["actions"].cpu(), g[f"{key}_actions"])
     torch.testing.assert_close(out["log_likelihood"].cpu()[same], g[f"{key}_logprobs"][same], rtol=RTOL, atol=ATOL_LP)
     torch.testing.assert_close(out["reward"].cpu()[same], g[f"{key}_reward"][same], rtol=RTOL, atol=1e-6)
-    assert same.all() if gemm == "cublas" else same.float().mean() >= 0.75
+    # N = 100: 100 starts x 100 selections per instance -- a genuine near-tie (each verified by the prefix oracle
+    # above) flips somewhere even with the strict-fp32 cache
+    exact = gemm == "cublas" and g["h"].shape[1] < 100
+    assert same.all() if exact else same.float().mean() >= 0.75
 
 
 @pytest.mark.parametrize("name", AM_FIX)
