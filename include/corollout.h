@@ -154,6 +154,7 @@ int co_select_action(const float* logits, const uint8_t* action_mask, const floa
  *     4: node_emb @ Wctx[:, E:2E]^T (tsp only: current-node table)
  */
 #define CO_ROLLOUT_FORCED_START 1 /* S>1: first action of start s is forced (multistart) */
+#define CO_ROLLOUT_NO_PREFETCH 2  /* diagnostic: do not prefetch the next instance's cache rows into L2 */
 
 typedef struct co_rollout_args {
   int32_t env_kind;     /* CO_ENV_*                                                    */

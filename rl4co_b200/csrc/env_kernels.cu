@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(256) tour_length_kernel(const float2* __restri
   // ordered tour: [depot?] a_0 .. a_{T-1}; edge k joins tour[k] and tour[(k+1) % L]
   const int L = T + (with_depot ? 1 : 0);
   float acc = 0.f;
+  // the coordinate row (N * 8 bytes) does not depend on the actions: pull its lines towards L1 now, so that the two
+  // HBM round trips (actions, then gathered coordinates) overlap instead of following each other
+  for (int ln = lane; ln * 16 < N; ln += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + ln * 16));
   // every action is read from HBM once: lane l holds tour[k] for k = base + l; its successor comes from lane l + 1
   // (the chunk's last lane reads one element ahead), so each 32-edge chunk costs one coalesced 256-byte load
   for (int base = 0; base < L; base += 32) {

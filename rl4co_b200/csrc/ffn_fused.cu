@@ -12,7 +12,8 @@
 //     FF2(j): Y += H W2_j^T           48 TS-form MMAs (A operand from TMEM, tools/micro/ts_mma_check.cu) -> TMEM Y
 //   Y + b2 + x, BN, store.
 // TMEM: H0 [0,128) H1 [128,256) H_lo [256,384) Y [384,512). W1_j / W2_j k-blocks ([128 x 32] hi + lo = 32 KB) stream from
-// L2 through a 2-stage cp.async ring in the fixed order FF1(0) FF1(1) FF2(0) FF1(2) FF2(1) FF1(3) FF2(2) FF2(3), so the
+// L2 through a 3-stage cp.async ring (two 32 KB blocks in flight: with one in flight the kernel was bound by the L2
+// round trip per block, 11.9 ms per layer measured) in the fixed order FF1(0) FF1(1) FF2(0) FF1(2) FF2(1) FF1(3) FF2(2) FF2(3), so the
 // epilogue of chunk j runs under the MMAs of FF1(j+1). Per tile: 384 MMAs x 64 cycles = 24.6 k cycles of tensor pipe and
 // 1 MB of weights from L2.  Replaces FF1 (5.4 ms) + four split-K FF2 passes (10.3 ms) per layer at M = 6.55 M.
 #include <stdint.h>
@@ -25,8 +26,8 @@ namespace ffn {
 constexpr int BM = 128, HID = 512, NJ = HID / 128, KB = 4;  // k-blocks of 32 per 128-wide reduction
 constexpr int TILE_B = 128 * 32 * 4;                         // one [128 x 32] operand tile = 16 KB
 constexpr int OFF_W = 2 * KB * TILE_B;                       // after x hi / lo
-constexpr int WST = 2;                                       // weight ring stages (hi + lo each)
-constexpr int SMEM_B = OFF_W + WST * 2 * TILE_B;             // 196 608
+constexpr int WST = 3;                                       // weight ring stages (hi + lo each): 2 blocks in flight
+constexpr int SMEM_B = OFF_W + WST * 2 * TILE_B;             // 229 376 (x 128 KB + 3 x 32 KB)
 constexpr int THREADS = 288;                                 // warps 0-3 producers, 4-7 epilogue, 8 issuer
 constexpr uint32_t SBO = 1024, COL_HLO = 256, COL_Y = 384;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -118,12 +119,12 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
   auto XFULL = [&]() { return b0; };                          // producers: x tile in SMEM                (128)
   auto XEMPTY = [&]() { return b0 + 8; };                     // FF1(3) retired: x tile reusable          (commit)
   auto WFULL = [&](int s) { return b0 + 8 * (2 + s); };       // producers: weight block landed           (128)
-  auto WEMPTY = [&](int s) { return b0 + 8 * (4 + s); };      // its MMAs retired                         (commit)
-  auto HFULL = [&](int a) { return b0 + 8 * (6 + a); };       // FF1(j) retired -> epilogue               (commit)
-  auto HPFULL = [&]() { return b0 + 8 * 8; };                 // epilogue: H_hi / H_lo of chunk j written (128)
-  auto HFREE = [&]() { return b0 + 8 * 9; };                  // FF2(j) retired: H[j & 1] and H_lo free   (commit)
-  auto YFULL = [&]() { return b0 + 8 * 10; };                 // FF2(3) retired                           (commit)
-  auto YEMPTY = [&]() { return b0 + 8 * 11; };                // epilogue read Y                          (128)
+  auto WEMPTY = [&](int s) { return b0 + 8 * (5 + s); };      // its MMAs retired                         (commit)
+  auto HFULL = [&](int a) { return b0 + 8 * (8 + a); };       // FF1(j) retired -> epilogue               (commit)
+  auto HPFULL = [&]() { return b0 + 8 * 10; };                // epilogue: H_hi / H_lo of chunk j written (128)
+  auto HFREE = [&]() { return b0 + 8 * 11; };                 // FF2(j) retired: H[j & 1] and H_lo free   (commit)
+  auto YFULL = [&]() { return b0 + 8 * 12; };                 // FF2(3) retired                           (commit)
+  auto YEMPTY = [&]() { return b0 + 8 * 13; };                // epilogue read Y                          (128)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 8) {
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
   if (tid == 0) {
     auto init = [&](uint32_t bar, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); };
     init(XFULL(), 128); init(XEMPTY(), 1); init(HPFULL(), 128); init(HFREE(), 1); init(YFULL(), 1); init(YEMPTY(), 128);
-    for (int s = 0; s < 2; ++s) { init(WFULL(s), 128); init(WEMPTY(s), 1); init(HFULL(s), 1); }
+    for (int s = 0; s < WST; ++s) { init(WFULL(s), 128); init(WEMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) init(HFULL(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   tc_before();
@@ -170,11 +172,11 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
       }
       fence_async();
       bar_arrive(XFULL());
-      // weight blocks: cp.async straight into the swizzled tile (weights are pre-split, no conversion); one block of
-      // look-ahead: block b + 1 is in flight while block b is waited for and published
+      // weight blocks: cp.async straight into the swizzled tile (weights are pre-split, no conversion); two blocks of
+      // look-ahead: blocks b + 1 and b + 2 are in flight while block b is waited for and published
       auto issue = [&](uint32_t k, int b) {
-        const int st = k & 1;
-        bar_wait(WEMPTY(st), ((k >> 1) & 1) ^ 1);
+        const int st = k % WST;
+        bar_wait(WEMPTY(st), ((k / WST) & 1) ^ 1);
         const WBlock w = wblock(b);
         const float* hi = w.ff2 ? g.w2hi + (size_t)w.j * 128 + w.kb * 32 : g.w1hi + (size_t)w.j * 128 * 128 + w.kb * 32;
         const float* lo = w.ff2 ? g.w2lo + (size_t)w.j * 128 + w.kb * 32 : g.w1lo + (size_t)w.j * 128 * 128 + w.kb * 32;
@@ -190,15 +192,18 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
       issue(wb, 0);
+      issue(wb + 1, 1);
       for (int b = 0; b < 32; ++b) {
-        if (b + 1 < 32) {
-          issue(wb + 1, b + 1);
+        if (b + 2 < 32) {
+          issue(wb + 2, b + 2);
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+        } else if (b + 1 < 32) {
           asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
           asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         fence_async();
-        bar_arrive(WFULL(wb & 1));
+        bar_arrive(WFULL(wb % WST));
         ++wb;
       }
     }
@@ -208,8 +213,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
       uint32_t wb = 0, hc = 0;  // weight blocks consumed, hidden chunks started (over all tiles)
       auto gemm_block = [&](bool ts, uint32_t d, uint32_t a_tmem, bool first) {
         // one k-block (32) = 4 k-steps x {hi.hi, lo.hi, hi.lo}; A = x tiles (SS) or H_hi / H_lo columns (TS)
-        const int st = wb & 1;
-        bar_wait(WFULL(st), (wb >> 1) & 1);
+        const int st = wb % WST;
+        bar_wait(WFULL(st), (wb / WST) & 1);
         tc_after();
         const uint32_t bhi = s32(sW + (2 * st) * TILE_B), blo = bhi + TILE_B;
         const int kb = wblock(wb & 31).kb;

@@ -40,6 +40,7 @@ extern "C" int co_rollout(const co_rollout_args* args, void* stream) {
   static const bool use_ms = !(getenv("CO_ROLLOUT_MS") && atoi(getenv("CO_ROLLOUT_MS")) == 0);
   const bool ms = use_ms && A.num_starts > 1;
   if (A.cache_width == 0) A.cache_width = co_cache_width(A.env_kind);
+  if (getenv("CO_ROLLOUT_PREFETCH") && atoi(getenv("CO_ROLLOUT_PREFETCH")) == 0) A.flags |= CO_ROLLOUT_NO_PREFETCH;
   if (A.env_kind == CO_ENV_TSP) {
     if (!A.q_placeholder) return fail(CO_ERR_BAD_ARG, "co_rollout: q_placeholder required for tsp%s");
     if (A.T_max < A.N) return fail(CO_ERR_BAD_ARG, "co_rollout: T_max < N%s");

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 #pragma unroll
     for (int k = 0; k < SPL; ++k) { WK[k] = 0.f; FK[k] = 0.f; }
     if (ENV == CO_ENV_CVRP) head_dot(sm.wcap, WK);
-    if (b + (int)gridDim.x < B_inst) {  // next instance's cache rows -> L2 while this episode runs
+    if (!(A.flags & CO_ROLLOUT_NO_PREFETCH) && b + (int)gridDim.x < B_inst) {  // next instance's cache rows -> L2
       const char* nxt = reinterpret_cast<const char*>(A.cache + (size_t)(b + gridDim.x) * N * CW);
       const int lines = (N * CW * 4 + 127) >> 7;
       for (int i = tid; i < lines; i += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)i << 7)));

@@ -26,6 +26,7 @@ The concatenated weight and its tf32 hi / lo split are cached per weight version
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -169,6 +170,8 @@ class FusedAttentionModelDecoder(nn.Module):
         multistart kernel); default: only when `num_starts` > 1."""
         if first_table is None:
             first_table = num_starts > 1
+        if os.environ.get("CO_TSP_FIRST_TABLE") == "1":  # diagnostic: always use the 5E layout
+            first_table = True
         first_table = bool(first_table) and self.env_name == "tsp"
         needs_grad = torch.is_grad_enabled() and (embeddings.requires_grad or any(
             p.requires_grad for p in (self.project_node_embeddings.weight, self.pointer.project_out.weight,

@@ -595,7 +595,12 @@ def test_pomo_config_c4_vs_reference_fixture(golden, dev):
     enc = pol.encoder
     pol.encoder = _FixedEncoder(h_cpu.to(dev))
     with torch.inference_mode():
-        ev = pol(td, env, phase="test", actions=ref_actions.to(dev), return_sum_log_likelihood=False)
+        # teacher forcing works on the expanded batch (one row per trajectory), like the reference's Evaluate
+        from rl4co_b200.ops import batchify
+
+        pol.encoder = _FixedEncoder(batchify(h_cpu.to(dev), N))
+        ev = pol(batchify(td, N), env, phase="test", actions=ref_actions.to(dev), return_sum_log_likelihood=False)
+        pol.encoder = _FixedEncoder(h_cpu.to(dev))
         free = pol(td, env, phase="test", decode_type="multistart_greedy", num_starts=N, return_sum_log_likelihood=False)
     ll = ev["log_likelihood"].cpu()
     torch.testing.assert_close(ll[:, 1:].sum(1), g["logprobs_sum"], rtol=RTOL, atol=5e-5)
