@@ -42,6 +42,7 @@ extern "C" {
 /* environment kinds (env.name in the reference: "tsp", "cvrp") */
 #define CO_ENV_TSP 0
 #define CO_ENV_CVRP 1
+#define CO_ENV_SDVRP 2 /* split-delivery VRP: VRP context + dynamic embedding; stepping kernels only */
 
 /* action-selection modes (rl4co/utils/decoding.py:426-461) */
 #define CO_SELECT_GREEDY 0       /* Greedy._step: argmax, first index on ties            */
@@ -84,6 +85,16 @@ int co_cvrp_step(const int64_t* action, const float* demand, const float* vehicl
  *   reward[b] = - sum_t || x[a_{t+1}] - x[a_t] ||_2 over the cyclic tour; with_depot=1
  *   prepends node 0 (CVRP).  locs [B_locs,N,2]; actions [B,T]; trajectory j uses
  *   instance j % B_locs (multistart / augmentation share locs). */
+/* SDVRPEnv (rl4co/envs/routing/sdvrp/env.py): `demand_with_depot` [B,N] f32 is the dynamic state (depot entry 0).
+ * co_sdvrp_step = _step :55-82 (deliver min(demand, capacity - used), scatter_add, done) + get_action_mask :110-116;
+ * outputs may alias inputs (in-place update). */
+int co_sdvrp_action_mask(const float* demand_with_depot, const float* used_capacity,
+                         const float* vehicle_capacity, const int64_t* current_node, uint8_t* mask_out,
+                         int B, int N, void* stream);
+int co_sdvrp_step(const int64_t* action, const float* demand_in, float* demand_out,
+                  const float* vehicle_capacity, const float* used_in, float* used_out,
+                  int64_t* current_node, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream);
+
 int co_tour_length(const float* locs, const int64_t* actions, float* reward, int B,
                    int B_locs, int N, int T, int with_depot, void* stream);
 
@@ -104,6 +115,12 @@ typedef struct co_decoder_weights {
   const float* w_placeholder;     /* [2E] (tsp only, else NULL)                       */
   const float* project_out_t;     /* [E, E] transposed pointer.project_out.weight, or  */
                                   /* NULL when logit_key is pre-multiplied by it       */
+  /* dynamic embedding (sdvrp: SDVRPDynamicEmbedding, nn/env_embeddings/dynamic.py:60-78; am/decoder.py:142-154):
+   * glimpse_key / glimpse_val / logit_key of node n get + dynamic_feature[j, n] * dynamic_w[0:E | E:2E | 2E:3E].
+   * Both NULL for static embeddings (tsp, cvrp). */
+  const float* dynamic_w;         /* [3E] = projection.weight[:, 0]; the logit third folded with project_out   */
+                                  /* (W_out^T w_l) when project_out_t == NULL                                   */
+  const float* dynamic_feature;   /* [B_traj, N] per-step node feature (sdvrp: remaining demand, depot = 0)     */
 } co_decoder_weights;
 
 /* AttentionModelDecoder.forward (rl4co/models/zoo/am/decoder.py:156-193):

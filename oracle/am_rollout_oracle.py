@@ -221,14 +221,84 @@ def cvrp_check_solution(st, actions):
         assert (used <= st["vehicle_capacity"][:, 0] + 1e-5).all(), "Used more than capacity"
 
 
-ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset}
-ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step}
+# --------------------------------------------------------------------------- SDVRP env (sibling env)
+# reference: rl4co/envs/routing/sdvrp/env.py
+
+
+def sdvrp_action_mask(st):
+    """sdvrp/env.py:110-116"""
+    mask_loc = (st["demand_with_depot"][..., 1:] == 0) | (st["used_capacity"] >= st["vehicle_capacity"])
+    mask_depot = (st["current_node"] == 0).squeeze(-1) & ((mask_loc == 0).int().sum(-1) > 0)
+    return ~torch.cat((mask_depot[..., None], mask_loc), -1)
+
+
+def sdvrp_reset(depot, locs, demand, vehicle_capacity: float = 1.0):
+    """sdvrp/env.py:84-108"""
+    B = locs.shape[0]
+    dev = locs.device
+    st = {
+        "locs": torch.cat((depot[:, None, :], locs), -2),
+        "demand": demand,
+        "demand_with_depot": torch.cat((torch.zeros_like(demand[..., 0:1]), demand), -1),
+        "current_node": torch.zeros(B, 1, dtype=torch.long, device=dev),
+        "used_capacity": torch.zeros(B, 1, device=dev),
+        "vehicle_capacity": torch.full((B, 1), vehicle_capacity, device=dev),
+    }
+    st["action_mask"] = sdvrp_action_mask(st)
+    st["done"] = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+    return st
+
+
+def sdvrp_step(state, action):
+    """sdvrp/env.py:55-82: deliver min(remaining demand, remaining capacity); nodes may be revisited"""
+    st = dict(state)
+    current_node = action[:, None]
+    selected_demand = gather_by_index(st["demand_with_depot"], current_node, dim=-1, squeeze=False)[..., :1]
+    delivered = torch.min(selected_demand, st["vehicle_capacity"] - st["used_capacity"])
+    used_capacity = (st["used_capacity"] + delivered) * (current_node != 0).float()
+    demand_with_depot = st["demand_with_depot"].scatter_add(-1, current_node, -delivered)
+    done = ~(demand_with_depot > 0).any(-1)
+    st.update(demand_with_depot=demand_with_depot, current_node=current_node, used_capacity=used_capacity,
+              reward=torch.zeros_like(done), done=done, action=action)
+    st["action_mask"] = sdvrp_action_mask(st)
+    return st
+
+
+def sdvrp_check_solution(st, actions):
+    """sdvrp/env.py:118-139"""
+    demands = torch.cat((-st["vehicle_capacity"], st["demand"]), 1).clone()
+    rng = torch.arange(demands.shape[0])
+    used_cap = torch.zeros_like(st["demand"][..., 0])
+    a_prev = None
+    for a in actions.transpose(0, 1):
+        assert a_prev is None or (demands[((a_prev == 0) & (a == 0)), :] == 0).all(), \
+            "Cannot visit depot twice if any nonzero demand"
+        d = torch.min(demands[rng, a], st["vehicle_capacity"].squeeze(-1) - used_cap)
+        demands[rng, a] -= d
+        used_cap += d
+        used_cap[a == 0] = 0
+        a_prev = a
+    assert (demands == 0).all(), "All demand must be satisfied"
+
+
+def sdvrp_dynamic_embedding(weights, st):
+    """nn/env_embeddings/dynamic.py:60-78 (SDVRPDynamicEmbedding): Linear(1 -> 3E, no bias) of the remaining demand,
+    depot entry forced to 0; chunks add to glimpse_key / glimpse_val / logit_key (am/decoder.py:142-154)."""
+    d = st["demand_with_depot"][..., None].clone()
+    d[..., 0, :] = 0
+    return F.linear(d, _w(weights, "dynamic_embedding.projection.weight")).chunk(3, dim=-1)
+
+
+ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset, "sdvrp": sdvrp_reset}
+ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step, "sdvrp": sdvrp_step}
 
 
 def env_reset(env_name, inst):
-    """inst: dict with 'locs' (tsp) or 'depot','locs','demand' (cvrp; generator output keys)."""
+    """inst: dict with 'locs' (tsp) or 'depot','locs','demand' (cvrp / sdvrp; generator output keys)."""
     if env_name == "tsp":
         return tsp_reset(inst["locs"])
+    if env_name == "sdvrp":
+        return sdvrp_reset(inst["depot"], inst["locs"], inst["demand"])
     return cvrp_reset(inst["depot"], inst["locs"], inst["demand"])
 
 
@@ -251,6 +321,7 @@ def generate_instances(env_name, batch, num_loc, generator=None):
 
     if env_name == "tsp":
         return {"locs": uni((batch, num_loc, 2), 0.0, 1.0)}
+    # cvrp and sdvrp share CVRPGenerator (sdvrp/env.py:47-54)
     locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
     demand = uni((batch, num_loc), 0.0, 9.0)
     demand = (demand.int() + 1).float()
@@ -319,11 +390,15 @@ def decoder_forward(weights, env_name, st, cache, num_starts=0, faithful_copies=
     two_batch_dims = st["action_mask"].dim() == 3
     if two_batch_dims and isinstance(g, torch.Tensor):
         g = g.unsqueeze(1)
-    ctx = tsp_context(weights, emb, st) if env_name == "tsp" else vrp_context(weights, emb, st)
+    ctx = tsp_context(weights, emb, st) if env_name == "tsp" else vrp_context(weights, emb, st)  # cvrp, sdvrp
     q = ctx + g
     q = q.unsqueeze(1) if q.ndim == 2 else q
     K, V, L = cache["glimpse_key"], cache["glimpse_val"], cache["logit_key"]
-    if faithful_copies:  # `stat + 0` materialises 3 copies per step, am/decoder.py:149-152
+    if env_name == "sdvrp":  # dynamic embedding, am/decoder.py:142-154
+        assert num_starts <= 1, "the sdvrp restatement covers single-start decoding"
+        dk, dv, dl = sdvrp_dynamic_embedding(weights, st)
+        K, V, L = K + dk, V + dv, L + dl
+    elif faithful_copies:  # `stat + 0` materialises 3 copies per step, am/decoder.py:149-152
         K, V, L = K + 0, V + 0, L + 0
     mask = st["action_mask"]
     logits = pointer_logits(weights, q, K, V, L, mask)

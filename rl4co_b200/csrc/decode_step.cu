@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(128) pointer_logits_kernel(
     const float* __restrict__ Vc, const float* __restrict__ Lc, const uint8_t* __restrict__ mask,
     const int64_t* __restrict__ first_node, const int64_t* __restrict__ current_node,
     const int64_t* __restrict__ istep, const float* __restrict__ used, const float* __restrict__ cap,
+    const float* __restrict__ dyn_w, const float* __restrict__ dyn_feat,
     float* __restrict__ logits_out, int B_inst, int N, int ld) {
   extern __shared__ float sm[];
   float* ctx = sm;             // [2E] context input
@@ -30,6 +31,8 @@ __global__ void __launch_bounds__(128) pointer_logits_kernel(
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const float* hb = node_emb + (size_t)b * N * E;
   const uint8_t* mrow = mask + (size_t)j * N;
+  // dynamic embedding (am/decoder.py:142-154): key / value / logit-key rows of node n get + feat[n] * w
+  const float* frow = dyn_feat ? dyn_feat + (size_t)j * N : nullptr;
 
   int ctx_dim;
   if (ENV == CO_ENV_TSP) {
@@ -56,8 +59,14 @@ __global__ void __launch_bounds__(128) pointer_logits_kernel(
   __syncthreads();
   {  // scores[h][n] = q_h . K_h[n] / sqrt(16), masked -> -inf
     const float4 qv = reinterpret_cast<const float4*>(q)[lane];
+    float4 wk = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (frow) wk = reinterpret_cast<const float4*>(dyn_w)[lane];
     for (int n = w; n < N; n += 4) {
-      const float4 kv = reinterpret_cast<const float4*>(Kc + ((size_t)b * N + n) * ld)[lane];
+      float4 kv = reinterpret_cast<const float4*>(Kc + ((size_t)b * N + n) * ld)[lane];
+      if (frow) {
+        const float f = frow[n];
+        kv.x = kv.x + f * wk.x; kv.y = kv.y + f * wk.y; kv.z = kv.z + f * wk.z; kv.w = kv.w + f * wk.w;
+      }
       float p = qv.x * kv.x + qv.y * kv.y + qv.z * kv.z + qv.w * kv.w;
       p += __shfl_xor_sync(FULL, p, 1);
       p += __shfl_xor_sync(FULL, p, 2);
@@ -85,7 +94,12 @@ __global__ void __launch_bounds__(128) pointer_logits_kernel(
     const float* s = sc + (t >> 4) * N;
     const float* vb = Vc + (size_t)b * N * ld + t;
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(s[n], vb[(size_t)n * ld], acc);
+    if (frow) {
+      const float wv = dyn_w[E + t];
+      for (int n = 0; n < N; ++n) acc = fmaf(s[n], vb[(size_t)n * ld] + frow[n] * wv, acc);
+    } else {
+      for (int n = 0; n < N; ++n) acc = fmaf(s[n], vb[(size_t)n * ld], acc);
+    }
     o[t] = acc;
   }
   __syncthreads();
@@ -101,8 +115,14 @@ __global__ void __launch_bounds__(128) pointer_logits_kernel(
   __syncthreads();
   {  // logits[n] = glimpse . L[n] / sqrt(E)
     const float4 gv = reinterpret_cast<const float4*>(g2)[lane];
+    float4 wl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (frow) wl = reinterpret_cast<const float4*>(dyn_w + 2 * E)[lane];
     for (int n = w; n < N; n += 4) {
-      const float4 lv = reinterpret_cast<const float4*>(Lc + ((size_t)b * N + n) * ld)[lane];
+      float4 lv = reinterpret_cast<const float4*>(Lc + ((size_t)b * N + n) * ld)[lane];
+      if (frow) {
+        const float f = frow[n];
+        lv.x = lv.x + f * wl.x; lv.y = lv.y + f * wl.y; lv.z = lv.z + f * wl.z; lv.w = lv.w + f * wl.w;
+      }
       float p = gv.x * lv.x + gv.y * lv.y + gv.z * lv.z + gv.w * lv.w;
       p = warp_sum(p);
       if (lane == 0) logits_out[(size_t)j * N + n] = p / 11.313708498984761f;
@@ -194,8 +214,11 @@ extern "C" int co_pointer_logits(int env_kind, const co_decoder_weights* w, cons
     }
     pointer_logits_kernel<CO_ENV_TSP><<<B_traj, 128, smem, st>>>(
         w->project_context_t, w->w_placeholder, w->project_out_t, node_emb, graph_ctx, glimpse_key, glimpse_val,
-        logit_key, action_mask, first_node, current_node, i, nullptr, nullptr, logits_out, B_inst, N, ld);
-  } else if (env_kind == CO_ENV_CVRP) {
+        logit_key, action_mask, first_node, current_node, i, nullptr, nullptr, nullptr, nullptr, logits_out, B_inst, N, ld);
+  } else if (env_kind == CO_ENV_CVRP || env_kind == CO_ENV_SDVRP) {  // both use VRPContext (context.py:26,137-149)
+    if ((w->dynamic_w == nullptr) != (w->dynamic_feature == nullptr))
+      return fail(CO_ERR_BAD_ARG, "co_pointer_logits: dynamic_w and dynamic_feature go together%s");
+    if (env_kind == CO_ENV_SDVRP && !w->dynamic_w) return fail(CO_ERR_BAD_ARG, "co_pointer_logits: sdvrp needs the dynamic embedding%s");
     if (!used_capacity || !vehicle_capacity) return fail(CO_ERR_BAD_ARG, "co_pointer_logits: cvrp state missing%s");
     static PerDeviceOnce once;
     bool& attr = once.flag();
@@ -205,7 +228,8 @@ extern "C" int co_pointer_logits(int env_kind, const co_decoder_weights* w, cons
     }
     pointer_logits_kernel<CO_ENV_CVRP><<<B_traj, 128, smem, st>>>(
         w->project_context_t, nullptr, w->project_out_t, node_emb, graph_ctx, glimpse_key, glimpse_val, logit_key,
-        action_mask, nullptr, current_node, nullptr, used_capacity, vehicle_capacity, logits_out, B_inst, N, ld);
+        action_mask, nullptr, current_node, nullptr, used_capacity, vehicle_capacity, w->dynamic_w, w->dynamic_feature,
+        logits_out, B_inst, N, ld);
   } else {
     return fail(CO_ERR_BAD_ARG, "co_pointer_logits: unknown env kind%s %lld", "", env_kind);
   }

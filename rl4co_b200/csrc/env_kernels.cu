@@ -6,6 +6,7 @@
 //   co_tour_length       <- tsp/env.py:150-156, cvrp/env.py:138-147, rl4co/utils/ops.py:54-90
 //   co_check_tours       <- tsp/env.py:158-164, cvrp/env.py:149-177
 //   co_reward_stats      <- rl4co/models/rl/reinforce/baselines.py:75-81 (mean baseline)
+//   co_sdvrp_step / co_sdvrp_action_mask <- rl4co/envs/routing/sdvrp/env.py:55-82,110-116 (sibling env: split deliveries)
 #include "co_common.cuh"
 
 namespace co {
@@ -136,6 +137,63 @@ __global__ void __launch_bounds__(256) cvrp_step_kernel(const int64_t* __restric
     done[row] = (cnt == N);
   }
   cvrp_mask_row(dem, used, cap[row], vo, a, mask_out + (size_t)row * N, N, lane);
+}
+
+// ---- SDVRP (rl4co/envs/routing/sdvrp/env.py): nodes may be revisited, the remaining demand is the dynamic state
+// get_action_mask, sdvrp/env.py:110-116: mask_loc = (demand == 0) | (used >= capacity); depot rule as in CVRP
+__device__ __forceinline__ void sdvrp_mask_row(const float* __restrict__ dwd, float used, float cap, int cur,
+                                               uint8_t* mask_out, int N, int lane) {
+  const bool full = used >= cap;
+  int any_free = 0;
+  for (int n = 1 + lane; n < N; n += 32) {
+    const bool masked = (dwd[n] == 0.0f) || full;
+    mask_out[n] = masked ? 0 : 1;
+    any_free |= masked ? 0 : 1;
+  }
+  any_free = __any_sync(FULL, any_free);
+  if (lane == 0) mask_out[0] = ((cur == 0) && any_free) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) sdvrp_mask_kernel(const float* __restrict__ dwd, const float* __restrict__ used,
+                                                          const float* __restrict__ cap,
+                                                          const int64_t* __restrict__ current_node, uint8_t* mask_out,
+                                                          int B, int N) {
+  int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  sdvrp_mask_row(dwd + (size_t)row * N, used[row], cap[row], (int)current_node[row], mask_out + (size_t)row * N, N, lane);
+}
+
+// _step, sdvrp/env.py:55-82: delivered = min(demand[a], capacity - used); used = (used + delivered) * (a != 0);
+// demand[a] -= delivered (scatter_add of -delivered); done = no positive demand left; then the mask
+__global__ void __launch_bounds__(256) sdvrp_step_kernel(const int64_t* __restrict__ action, const float* dwd_in,
+                                                          float* dwd_out, const float* __restrict__ cap,
+                                                          const float* used_in, float* used_out, int64_t* current_node,
+                                                          uint8_t* done, uint8_t* mask_out, int B, int N) {
+  int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int a = (int)action[row];
+  const float* di = dwd_in + (size_t)row * N;
+  float* dout = dwd_out + (size_t)row * N;
+  const float c = cap[row], u = used_in[row];
+  const float delivered = fminf(di[a], c - u);
+  const float used = (u + delivered) * (a != 0 ? 1.0f : 0.0f);
+  int positive = 0;
+  for (int n = lane; n < N; n += 32) {
+    float v = di[n];
+    if (n == a) v = v + (-delivered);  // scatter_add(-1, a, -delivered)
+    dout[n] = v;
+    positive |= (v > 0.0f) ? 1 : 0;
+  }
+  positive = __any_sync(FULL, positive);
+  __syncwarp();
+  if (lane == 0) {
+    used_out[row] = used;
+    current_node[row] = a;
+    done[row] = positive ? 0 : 1;
+  }
+  sdvrp_mask_row(dout, used, c, a, mask_out + (size_t)row * N, N, lane);
 }
 
 // reward = -(cyclic tour length); one warp per trajectory, lanes stride the T edges.
@@ -278,6 +336,31 @@ extern "C" int co_cvrp_step(const int64_t* action, const float* demand, const fl
                                                                    used_out, visited_in, visited_out,
                                                                    current_node, done, mask_out, B, N);
   return check_launch("co_cvrp_step");
+}
+
+extern "C" int co_sdvrp_action_mask(const float* demand_with_depot, const float* used_capacity,
+                                    const float* vehicle_capacity, const int64_t* current_node, uint8_t* mask_out,
+                                    int B, int N, void* stream) {
+  if (!demand_with_depot || !used_capacity || !vehicle_capacity || !current_node || !mask_out)
+    return fail(CO_ERR_BAD_ARG, "co_sdvrp_action_mask: null pointer%s");
+  if (B < 0 || N < 2) return fail(CO_ERR_BAD_ARG, "co_sdvrp_action_mask: bad shape%s B=%lld N=%lld", "", B, N);
+  if (B == 0) return CO_OK;
+  sdvrp_mask_kernel<<<rows_grid(B), 256, 0, (cudaStream_t)stream>>>(demand_with_depot, used_capacity, vehicle_capacity,
+                                                                    current_node, mask_out, B, N);
+  return check_launch("co_sdvrp_action_mask");
+}
+
+extern "C" int co_sdvrp_step(const int64_t* action, const float* demand_in, float* demand_out,
+                             const float* vehicle_capacity, const float* used_in, float* used_out,
+                             int64_t* current_node, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream) {
+  if (!action || !demand_in || !demand_out || !vehicle_capacity || !used_in || !used_out || !current_node || !done ||
+      !mask_out)
+    return fail(CO_ERR_BAD_ARG, "co_sdvrp_step: null pointer%s");
+  if (B < 0 || N < 2) return fail(CO_ERR_BAD_ARG, "co_sdvrp_step: bad shape%s B=%lld N=%lld", "", B, N);
+  if (B == 0) return CO_OK;
+  sdvrp_step_kernel<<<rows_grid(B), 256, 0, (cudaStream_t)stream>>>(action, demand_in, demand_out, vehicle_capacity,
+                                                                    used_in, used_out, current_node, done, mask_out, B, N);
+  return check_launch("co_sdvrp_step");
 }
 
 extern "C" int co_tour_length(const float* locs, const int64_t* actions, float* reward, int B, int B_locs,

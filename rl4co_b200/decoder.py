@@ -12,10 +12,13 @@ What differs is the cache layout.  ``_precompute_cache`` does ONE GEMM
     2  logit_key @ project_out.weight  (rows 2E:3E, folded with pointer.project_out so the
                                         per-step 128x128 projection disappears:
                                         logits = heads . (L W_out)[n] == (W_out heads) . L[n])
-    [3 embeddings @ Wctx[:, :E]^T      tsp, `first_table=True` only: first-node half of
-                                        project_context as a table -- the multistart kernel reads
-                                        one row per start; single-start rollouts leave it out and
-                                        do one 128x128 GEMV per episode in the kernel instead]
+    [3 embeddings @ Wctx[:, :E]^T      tsp, `first_table=True` (default): first-node half of
+                                        project_context as a table -- the multistart kernel reads one
+                                        row per start, a single-start episode one row.  `first_table=
+                                        False` (CO_TSP_FIRST_TABLE=0) leaves the block out and the
+                                        kernel does one 128x128 GEMV per episode instead: 20 % less GEMM
+                                        output, but measured 1.1 ms SLOWER per 65 536 x 100 step
+                                        (GEMM -1.4 ms, rollout kernel +2.5 ms), so it is not the default]
     last  embeddings @ Wctx_cur^T      current-node part of project_context (tsp: columns E:2E,
                                         cvrp: columns 0:E)
 
@@ -49,6 +52,15 @@ class _ContextEmbedding(nn.Module):
         self.project_context = nn.Linear(step_context_dim, embed_dim, bias=False)
         if env_name == "tsp":
             self.W_placeholder = nn.Parameter(torch.Tensor(2 * embed_dim).uniform_(-1, 1))
+
+
+class _DynamicEmbedding(nn.Module):
+    """Parameter holder named like SDVRPDynamicEmbedding (nn/env_embeddings/dynamic.py:60-78): Linear(1 -> 3E, no bias)
+    of the remaining demand, added to glimpse_key / glimpse_val / logit_key every step (am/decoder.py:142-154)."""
+
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        self.projection = nn.Linear(1, 3 * embed_dim, bias=False)
 
 
 class _Pointer(nn.Module):
@@ -112,7 +124,7 @@ class FusedAttentionModelDecoder(nn.Module):
         if embed_dim != E or num_heads != native.NUM_HEADS:
             raise NotImplementedError(f"kernels are instantiated for embed_dim={E}, num_heads={native.NUM_HEADS}")
         if env_name not in native.ENV_KIND:
-            raise NotImplementedError(f"env {env_name!r} is outside the fused path (tsp, cvrp)")
+            raise NotImplementedError(f"env {env_name!r} is outside the fused path (tsp, cvrp, sdvrp)")
         for arg, val, ok in (("context_embedding", context_embedding, None), ("dynamic_embedding", dynamic_embedding, None),
                              ("pointer", pointer, None), ("moe_kwargs", moe_kwargs, None), ("mask_inner", mask_inner, True),
                              ("out_bias_pointer_attn", out_bias_pointer_attn, False), ("linear_bias", linear_bias, False)):
@@ -120,12 +132,14 @@ class FusedAttentionModelDecoder(nn.Module):
                 raise NotImplementedError(f"{arg}={val!r} is not supported by the fused decoder")
         self.env_name, self.embed_dim, self.num_heads = env_name, embed_dim, num_heads
         self.context_embedding = _ContextEmbedding(env_name, embed_dim)
+        self.is_dynamic_embedding = env_name == "sdvrp"
+        if self.is_dynamic_embedding:
+            self.dynamic_embedding = _DynamicEmbedding(embed_dim)
         self.pointer = _Pointer(embed_dim)
         self.project_node_embeddings = nn.Linear(embed_dim, 3 * embed_dim, bias=False)
         self.project_fixed_context = nn.Linear(embed_dim, embed_dim, bias=False)
         self.use_graph_context = use_graph_context
         self.check_nan = check_nan
-        self.is_dynamic_embedding = False
         #: "tf32x3": hand-written tcgen05 3xTF32 GEMM (fp32-class accuracy, inference / no-grad only);
         #: "cublas": torch.nn.functional.linear (strict fp32 SIMT; always used when autograd is on)
         self.cache_gemm = cache_gemm
@@ -166,12 +180,10 @@ class FusedAttentionModelDecoder(nn.Module):
 
     def _precompute_cache(self, embeddings: torch.Tensor, num_starts: int = 0,
                           first_table: bool | None = None) -> FusedPrecomputedCache:
-        """am/decoder.py:201-228.  `first_table` (tsp): include the first-node context table (needed by the
-        multistart kernel); default: only when `num_starts` > 1."""
+        """am/decoder.py:201-228.  `first_table` (tsp): include the first-node context table (required by the
+        multistart kernel); default True, CO_TSP_FIRST_TABLE=0 selects the narrow layout for single-start calls."""
         if first_table is None:
-            first_table = num_starts > 1
-        if os.environ.get("CO_TSP_FIRST_TABLE") == "1":  # diagnostic: always use the 5E layout
-            first_table = True
+            first_table = num_starts > 1 or os.environ.get("CO_TSP_FIRST_TABLE", "1") != "0"
         first_table = bool(first_table) and self.env_name == "tsp"
         needs_grad = torch.is_grad_enabled() and (embeddings.requires_grad or any(
             p.requires_grad for p in (self.project_node_embeddings.weight, self.pointer.project_out.weight,
@@ -215,6 +227,12 @@ class FusedAttentionModelDecoder(nn.Module):
             keep.append(wp)
             w.w_placeholder = wp.data_ptr()
         w.project_out_t = None  # logit key is folded
+        if self.is_dynamic_embedding:
+            # [wk | wv | W_out^T wl]: the logit third folded like the logit key itself (module docstring, block 2)
+            wd = self.dynamic_embedding.projection.weight.detach()[:, 0]
+            wdyn = torch.cat((wd[:2 * E], self.pointer.project_out.weight.detach().t() @ wd[2 * E:])).contiguous()
+            keep.append(wdyn)
+            w.dynamic_w = wdyn.data_ptr()
         w._keepalive = keep
         return w
 
@@ -235,8 +253,13 @@ class FusedAttentionModelDecoder(nn.Module):
                 cached.glimpse_val, cached.logit_key_folded, mask, td["first_node"].reshape(-1).contiguous(), cur,
                 td["i"].reshape(-1).contiguous(), None, None, B_traj, B_inst, N)
         else:
+            if self.is_dynamic_embedding:  # dynamic.py:71-73: the depot entry of the feature is forced to 0
+                feat = td["demand_with_depot"].reshape(B_traj, N).clone()
+                feat[:, 0] = 0
+                w._keepalive.append(feat)
+                w.dynamic_feature = feat.data_ptr()
             logits = native.pointer_logits(
-                "cvrp", w, cached.node_embeddings.contiguous(), cached.graph_context_or_none, cached.glimpse_key,
+                self.env_name, w, cached.node_embeddings.contiguous(), cached.graph_context_or_none, cached.glimpse_key,
                 cached.glimpse_val, cached.logit_key_folded, mask, None, cur, None,
                 td["used_capacity"].reshape(-1).contiguous(), td["vehicle_capacity"].reshape(-1).contiguous(),
                 B_traj, B_inst, N)

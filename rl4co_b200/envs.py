@@ -344,7 +344,84 @@ class FusedCVRPEnv(FusedEnvBase):
         return td_load
 
 
-ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv}
+class FusedSDVRPEnv(FusedCVRPEnv):
+    """CUDA drop-in for rl4co.envs.SDVRPEnv (rl4co/envs/routing/sdvrp/env.py:14-139): split deliveries -- a
+    customer may be visited several times, each visit delivers min(remaining demand, remaining capacity).  The
+    dynamic state is `demand_with_depot` [B, N]; it feeds the decoder's dynamic embedding
+    (nn/env_embeddings/dynamic.py:60-78).  Runs on the stepping kernels (co_sdvrp_step / co_sdvrp_action_mask,
+    co_pointer_logits with the dynamic term, co_select_action, co_tour_length)."""
+
+    name = "sdvrp"
+
+    def _reset(self, td: TensorDict, batch_size=None) -> TensorDict:
+        """sdvrp/env.py:84-108"""
+        device = td.device
+        td_reset = TensorDict(
+            {
+                "locs": torch.cat((td["depot"][..., None, :], td["locs"]), -2),
+                "demand": td["demand"],
+                "demand_with_depot": torch.cat((torch.zeros_like(td["demand"][..., 0:1]), td["demand"]), -1),
+                "current_node": torch.zeros(*batch_size, 1, dtype=torch.long, device=device),
+                "used_capacity": torch.zeros((*batch_size, 1), device=device),
+                "vehicle_capacity": torch.full((*batch_size, 1), self.generator.vehicle_capacity, device=device),
+            },
+            batch_size=batch_size,
+        )
+        if td_reset["demand"].is_cuda:
+            mask = self.get_action_mask(td_reset)
+        else:  # reset only allocates state: initial mask of sdvrp/env.py:110-116 (vehicle empty, at the depot)
+            free = td_reset["demand"] != 0
+            mask = torch.cat((~free.any(-1, keepdim=True), free), -1)
+        td_reset.set("action_mask", mask)
+        return td_reset
+
+    def _step(self, td: TensorDict) -> TensorDict:
+        """sdvrp/env.py:55-82 incl. the trailing get_action_mask, one kernel (co_sdvrp_step)."""
+        action = td["action"].contiguous()
+        B = action.shape[0]
+        d_in = td["demand_with_depot"].contiguous()
+        used_in = td["used_capacity"].contiguous()
+        d_out = d_in if self.inplace else torch.empty_like(d_in)
+        used_out = torch.empty_like(used_in)
+        current_node = torch.empty(B, 1, dtype=torch.int64, device=action.device)
+        done = torch.empty(B, dtype=torch.bool, device=action.device)
+        mask_out = torch.empty(B, d_in.shape[-1], dtype=torch.bool, device=action.device)
+        native.sdvrp_step(action, d_in, d_out, td["vehicle_capacity"].contiguous(), used_in, used_out, current_node,
+                          done, mask_out)
+        td.update({"demand_with_depot": d_out, "current_node": current_node, "used_capacity": used_out,
+                   "reward": torch.zeros_like(done), "done": done})
+        td.set("action_mask", mask_out)
+        return td
+
+    @staticmethod
+    def get_action_mask(td: TensorDict) -> torch.Tensor:
+        """sdvrp/env.py:110-116 (co_sdvrp_action_mask)"""
+        d = td["demand_with_depot"].contiguous()
+        mask = torch.empty(d.shape, dtype=torch.bool, device=d.device)
+        return native.sdvrp_action_mask(d, td["used_capacity"].contiguous(), td["vehicle_capacity"].contiguous(),
+                                        td["current_node"].contiguous(), mask)
+
+    @staticmethod
+    def check_solution_validity(td: TensorDict, actions: torch.Tensor) -> None:
+        """sdvrp/env.py:118-139: replay the deliveries; all demand must be served, no idle depot-depot move while
+        demand remains.  Validation path (host-synchronising asserts, like the reference); device tensors."""
+        cap = td["vehicle_capacity"].reshape(-1)
+        demands = torch.cat((-td["vehicle_capacity"].reshape(-1, 1), td["demand"]), 1).clone()
+        rng = torch.arange(demands.shape[0], device=demands.device)
+        used = torch.zeros_like(cap)
+        a_prev = None
+        for a in actions.transpose(0, 1):
+            if a_prev is not None:
+                assert (demands[(a_prev == 0) & (a == 0), :] == 0).all(), "Cannot visit depot twice if any nonzero demand"
+            d = torch.min(demands[rng, a], cap - used)
+            demands[rng, a] -= d
+            used = used + d
+            used[a == 0] = 0
+            a_prev = a
+        assert (demands == 0).all(), "All demand must be satisfied"
+
+
+ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv, "sdvrp": FusedSDVRPEnv}
 
 
 def _register_with_torchrl() -> bool:

@@ -27,7 +27,10 @@ HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
-ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP}
+ENV_SDVRP = 2
+ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP}
+#: environments the whole-episode kernel (co_rollout) is instantiated for; others take the stepping kernels
+ROLLOUT_ENVS = ("tsp", "cvrp")
 SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
 ROLLOUT_FORCED_START = 1
 EMBED_DIM, NUM_HEADS = 128, 8
@@ -37,6 +40,7 @@ EXPORTS = [
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
     "co_ffn_fused", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
+    "co_sdvrp_step", "co_sdvrp_action_mask",
 ]
 
 
@@ -45,7 +49,8 @@ class NativeLibraryError(RuntimeError):
 
 
 class DecoderWeights(Structure):
-    _fields_ = [("project_context_t", c_void_p), ("w_placeholder", c_void_p), ("project_out_t", c_void_p)]
+    _fields_ = [("project_context_t", c_void_p), ("w_placeholder", c_void_p), ("project_out_t", c_void_p),
+                ("dynamic_w", c_void_p), ("dynamic_feature", c_void_p)]
 
 
 class RolloutArgs(Structure):
@@ -125,6 +130,8 @@ def lib() -> ctypes.CDLL:
     L.co_cvrp_action_mask.argtypes = [c_void_p] * 6 + [c_int, c_int, c_void_p]
     L.co_cvrp_step.argtypes = [c_void_p] * 10 + [c_int, c_int, c_void_p]
     L.co_tour_length.argtypes = [c_void_p] * 3 + [c_int] * 5 + [c_void_p]
+    L.co_sdvrp_action_mask.argtypes = [c_void_p] * 5 + [c_int, c_int, c_void_p]
+    L.co_sdvrp_step.argtypes = [c_void_p] * 9 + [c_int, c_int, c_void_p]
     L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.co_cache_width.argtypes = [c_int]
@@ -239,6 +246,25 @@ def cvrp_step(action, demand, cap, used_in, used_out, visited_in, visited_out, c
                               _ptr(visited_in, U8, "visited_in"), _ptr(visited_out, U8, "visited_out"),
                               _ptr(current_node, I64, "current_node"), _bool_ptr(done, "done"),
                               _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_cvrp_step")
+
+
+@_on_device_of_first_tensor
+def sdvrp_action_mask(demand_with_depot, used, cap, current_node, mask_out):
+    B, N = demand_with_depot.shape
+    _check(lib().co_sdvrp_action_mask(_ptr(demand_with_depot, F32, "demand_with_depot"), _ptr(used, F32, "used_capacity"),
+                                      _ptr(cap, F32, "vehicle_capacity"), _ptr(current_node, I64, "current_node"),
+                                      _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_sdvrp_action_mask")
+    return mask_out
+
+
+@_on_device_of_first_tensor
+def sdvrp_step(action, demand_in, demand_out, cap, used_in, used_out, current_node, done, mask_out):
+    B, N = demand_in.shape
+    _check(lib().co_sdvrp_step(_ptr(action, I64, "action"), _ptr(demand_in, F32, "demand_in"),
+                               _ptr(demand_out, F32, "demand_out"), _ptr(cap, F32, "vehicle_capacity"),
+                               _ptr(used_in, F32, "used_in"), _ptr(used_out, F32, "used_out"),
+                               _ptr(current_node, I64, "current_node"), _bool_ptr(done, "done"),
+                               _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_sdvrp_step")
 
 
 @_on_device_of_first_tensor

@@ -84,8 +84,9 @@ class FusedAttentionModelPolicy(nn.Module):
         clip_ = decoding_kwargs.get("tanh_clipping", self.tanh_clipping)
         temp_ = decoding_kwargs.get("temperature", self.temperature)
         softmax_ok = clip_ > 0 and temp_ > 0 and 2.0 * clip_ / temp_ < 80.0
+        env_name_ = getattr(env, "name", self.env_name)
         use_fused = (decoding_kwargs.pop("fused_rollout", self.fused_rollout) and N <= native.rollout_max_nodes()
-                     and softmax_ok
+                     and softmax_ok and env_name_ in native.ROLLOUT_ENVS
                      and not filtered and decode_type != "beam_search"
                      and not return_entropy and not decoding_kwargs.get("store_all_logp", False)
                      and decoding_kwargs.get("mask_logits", self.mask_logits)
@@ -132,7 +133,7 @@ class FusedAttentionModelPolicy(nn.Module):
         B_traj = B * S
         T_max = N if env_name == "tsp" else 2 * (N - 1)
         # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
-        cached = self.decoder._precompute_cache(hidden, first_table=S > 1)
+        cached = self.decoder._precompute_cache(hidden, first_table=True if S > 1 else None)
 
         forced = None
         if decode_type == "evaluate":

@@ -37,7 +37,12 @@ def npy(x):
 
 
 def make_env(name, n, check=True):
-    Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    if name == "sdvrp":
+        import importlib
+
+        Env = importlib.import_module("rl4co.envs.routing.sdvrp.env").SDVRPEnv
+    else:
+        Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
     return Env(generator_params=dict(num_loc=n), check_solution=check)
 
 
@@ -60,14 +65,63 @@ def env_fixture(name, n, batch, seed):
         if name == "cvrp":
             visited.append(npy(td["visited"]))
             used.append(npy(td["used_capacity"]))
+        if name == "sdvrp":
+            visited.append(npy(td["demand_with_depot"]))  # the dynamic state of the split-delivery env
+            used.append(npy(td["used_capacity"]))
     actions = torch.stack(actions, 1)
     reward = env.get_reward(td, actions)  # runs check_solution_validity too
     out.update(actions=npy(actions), action_mask=np.stack(masks), done=np.stack(dones),
                current_node=np.stack(cur), reward=npy(reward))
     if name == "cvrp":
         out.update(visited=np.stack(visited), used_capacity=np.stack(used))
+    elif name == "sdvrp":
+        out.update(demand_with_depot=np.stack(visited), used_capacity=np.stack(used))
     else:
         out.update(first_node=npy(td["first_node"]), i=npy(td["i"]))
+    return out
+
+
+def sdvrp_am_fixture(n, batch, seed):
+    """SDVRP through the reference AttentionModelPolicy (VRPContext + SDVRPDynamicEmbedding, dynamic.py:60-78):
+    greedy, sampling with recorded noise, teacher-forced evaluation -- single-start decoding."""
+    torch.manual_seed(seed)
+    env = make_env("sdvrp", n)
+    pol = ref.AttentionModelPolicy(env_name="sdvrp", num_encoder_layers=1).eval()
+    with torch.no_grad():  # the default init of a Linear(1, 3E) is small next to the static keys: make it count
+        pol.decoder.dynamic_embedding.projection.weight.mul_(3.0)
+    out = {"w::" + k: npy(v) for k, v in pol.state_dict().items() if k.startswith("decoder.")}
+    td0 = env.generator(batch_size=[batch])
+    for k in td0.keys():
+        out[f"inst::{k}"] = npy(td0[k])
+    rec = Recorder(pol.decoder)
+    with torch.inference_mode():
+        td = env.reset(td0.clone())
+        h, _ = pol.encoder(td)
+        out["h"] = npy(h)
+        o = pol(td.clone(), env, phase="test", decode_type="greedy", return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        out.update(greedy_actions=npy(o["actions"]), greedy_logprobs=npy(o["log_likelihood"]),
+                   greedy_reward=npy(o["reward"]), greedy_logits=lg, greedy_masks=mk)
+        torch.manual_seed(seed + 1)
+        o = pol(td.clone(), env, phase="train", decode_type="sampling", return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        T = o["actions"].shape[1]
+        torch.manual_seed(seed + 1)
+        q = torch.stack([torch.empty(batch, lg.shape[-1]).exponential_(1) for _ in range(T)])
+        out.update(sampling_actions=npy(o["actions"]), sampling_logprobs=npy(o["log_likelihood"]),
+                   sampling_reward=npy(o["reward"]), sampling_noise=npy(q))
+        torch.manual_seed(seed + 2)
+        tdr = env.reset(td0.clone())
+        acts = []
+        while not tdr["done"].all():
+            tdr = ref.decoding.random_policy(tdr)
+            acts.append(tdr["action"].clone())
+            tdr = env.step(tdr)["next"]
+        acts = torch.stack(acts, 1)
+        o = pol(td.clone(), env, phase="train", actions=acts, return_sum_log_likelihood=False)
+        lg, mk = rec.pop()
+        out.update(eval_actions=npy(acts), eval_logprobs=npy(o["log_likelihood"]), eval_reward=npy(o["reward"]),
+                   eval_logits=lg)
     return out
 
 
@@ -297,6 +351,10 @@ def main():
         "am_tsp100": lambda: am_fixture("tsp", 100, 4, 204, ms_batch=1, lean=True),
         "am_cvrp100": lambda: am_fixture("cvrp", 100, 4, 205, ms_batch=1, lean=True),
         "pomo_tsp100": lambda: pomo_fixture(100, 2, 400),
+        "env_sdvrp20": lambda: env_fixture("sdvrp", 20, 16, 104),
+        "env_sdvrp50": lambda: env_fixture("sdvrp", 50, 8, 105),
+        "am_sdvrp20": lambda: sdvrp_am_fixture(20, 8, 206),
+        "am_sdvrp50": lambda: sdvrp_am_fixture(50, 4, 207),
         "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
         "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
         "layout": layout_fixture,

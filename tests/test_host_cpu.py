@@ -180,8 +180,8 @@ def test_fused_weight_blocks_cpu(golden):
     dec.load_state_dict(w)
     h = g["h"]
     with torch.inference_mode():
-        c = dec._precompute_cache(h, first_table=True)
-        c4 = dec._precompute_cache(h)  # default single-start layout: no first-node table
+        c = dec._precompute_cache(h)  # default layout: with the first-node table
+        c4 = dec._precompute_cache(h, first_table=False)  # narrow layout (per-episode GEMV in the kernel)
     E = 128
     assert c.rollout_cache.shape[-1] == 5 * E and c4.rollout_cache.shape[-1] == 4 * E
     kvl = torch.nn.functional.linear(h, w["project_node_embeddings.weight"])

@@ -7,8 +7,9 @@ import torch
 from oracle import am_rollout_oracle as O
 from conftest import env_of
 
-ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50"]
+ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50", "env_sdvrp20", "env_sdvrp50"]
 AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50", "am_tsp100", "am_cvrp100"]
+SD_FIX = ["am_sdvrp20", "am_sdvrp50"]  # sibling env (dynamic embedding), single-start decoding
 
 
 @pytest.mark.parametrize("name", ENV_FIX)
@@ -26,17 +27,22 @@ def test_env_mdp_bit_exact(golden, name):
         if env == "cvrp":
             assert torch.equal(st["visited"], g["visited"][t])
             assert torch.equal(st["used_capacity"], g["used_capacity"][t])
+        if env == "sdvrp":
+            assert torch.equal(st["demand_with_depot"], g["demand_with_depot"][t])
+            assert torch.equal(st["used_capacity"], g["used_capacity"][t])
     if env == "tsp":
         assert torch.equal(st["first_node"], g["first_node"])
         assert torch.equal(st["i"], g["i"])
         O.tsp_check_solution(actions)
+    elif env == "sdvrp":
+        O.sdvrp_check_solution(st, actions)
     else:
         O.cvrp_check_solution(st, actions)
     r = O.env_reward(env, st, actions)
     assert torch.equal(r, g["reward"])
 
 
-@pytest.mark.parametrize("name", AM_FIX)
+@pytest.mark.parametrize("name", AM_FIX + SD_FIX)
 def test_am_greedy(golden, name):
     g = golden(name)
     out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], "greedy", return_trace=True)
@@ -47,7 +53,7 @@ def test_am_greedy(golden, name):
     torch.testing.assert_close(out["reward"], g["greedy_reward"], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("name", AM_FIX)
+@pytest.mark.parametrize("name", AM_FIX + SD_FIX)
 def test_am_sampling_with_recorded_noise(golden, name):
     g = golden(name)
     q = g["sampling_noise"]
@@ -57,7 +63,7 @@ def test_am_sampling_with_recorded_noise(golden, name):
     torch.testing.assert_close(out["reward"], g["sampling_reward"], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("name", AM_FIX)
+@pytest.mark.parametrize("name", AM_FIX + SD_FIX)
 def test_am_teacher_forced(golden, name):
     g = golden(name)
     out = O.rollout(g.weights(), env_of(name), g.inst(), g["h"], actions=g["eval_actions"], return_trace=True)
