@@ -236,11 +236,15 @@ int co_gemm_tf32x3(const float* A, const float* Whi, const float* Wlo, float* C,
 /* Encoder feed-forward block in ONE kernel (the [M, 512] hidden activation never leaves the SM):
  *   out = ((x + relu(x W1^T + b1) W2^T + b2)) * scale + shift,  x [M,128], W1 [512,128], W2 [128,512]
  * = SkipConnection(MLP) + eval-mode BatchNorm of MultiHeadAttentionLayer (rl4co/models/nn/graph/attnnet.py:
- * 33-53, nn/mlp.py:45-60, nn/ops.py:9-15,30-46).  Weights pre-split with co_split_tf32; scale / shift NULL
- * (both) for no affine; ldx / ldo row strides in floats (% 4 == 0); 16-byte aligned pointers. */
-int co_ffn_fused(const float* x, const float* w1hi, const float* w1lo, const float* b1, const float* w2hi,
-                 const float* w2lo, const float* b2, const float* scale, const float* shift, float* out,
-                 int M, int ldx, int ldo, void* stream);
+ * 33-53, nn/mlp.py:45-60, nn/ops.py:9-15,30-46).  The weights are streamed by TMA bulk copies with cluster
+ * multicast from a pre-tiled image: co_ffn_tile_weights builds it (once per weight version) from the co_split_tf32
+ * parts of W1 and W2 into `wtiled` (co_ffn_tiled_weight_floats() floats, 128-byte aligned).
+ * scale / shift NULL (both) for no affine; ldx / ldo row strides in floats (% 4 == 0); 16-byte aligned pointers. */
+long co_ffn_tiled_weight_floats(void);
+int co_ffn_tile_weights(const float* w1hi, const float* w1lo, const float* w2hi, const float* w2lo, float* wtiled,
+                        void* stream);
+int co_ffn_fused(const float* x, const float* wtiled, const float* b1, const float* b2, const float* scale,
+                 const float* shift, float* out, int M, int ldx, int ldo, void* stream);
 
 /* ------------------------------------------------------------------ data path
  * On-device instance generation (Philox4x32-10 keyed by seed / offset; same seed -> same data on every GPU) and

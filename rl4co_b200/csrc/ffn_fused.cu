@@ -12,10 +12,18 @@
 //     FF2(j): Y += H W2_j^T           48 TS-form MMAs (A operand from TMEM, tools/micro/ts_mma_check.cu) -> TMEM Y
 //   Y + b2 + x, BN, store.
 // TMEM: H0 [0,128) H1 [128,256) H_lo [256,384) Y [384,512). W1_j / W2_j k-blocks ([128 x 32] hi + lo = 32 KB) stream from
-// L2 through a 3-stage cp.async ring (two 32 KB blocks in flight: with one in flight the kernel was bound by the L2
-// round trip per block, 11.9 ms per layer measured) in the fixed order FF1(0) FF1(1) FF2(0) FF1(2) FF2(1) FF1(3) FF2(2) FF2(3), so the
-// epilogue of chunk j runs under the MMAs of FF1(j+1). Per tile: 384 MMAs x 64 cycles = 24.6 k cycles of tensor pipe and
-// 1 MB of weights from L2.  Replaces FF1 (5.4 ms) + four split-K FF2 passes (10.3 ms) per layer at M = 6.55 M.
+// L2 in the fixed order FF1(0) FF1(1) FF2(0) FF1(2) FF2(1) FF1(3) FF2(2) FF2(3), so the epilogue of chunk j runs under
+// the MMAs of FF1(j+1). Per tile: 384 MMAs x 64 cycles = 24.6 k cycles of tensor pipe and 1 MB of weights.
+//
+// Weight stream = TMA bulk copies with CLUSTER MULTICAST.  The kernel runs as 2-CTA clusters; the weights are pre-tiled
+// once per weight version (co_ffn_tile_weights) into the exact shared-memory image of the operand tiles (K-major,
+// SWIZZLE_128B), block after block in issue order, so a block is two contiguous 16 KB pieces (hi, lo).  For every block
+// CTA r of the cluster issues ONE `cp.async.bulk ... .multicast::cluster` of piece r that lands in BOTH CTAs' rings and
+// signals both CTAs' "full" mbarriers (complete_tx); a ring stage is reused when the MMAs of BOTH CTAs have retired
+// (tcgen05.commit multicast onto both "empty" barriers).  Each SM therefore pulls 0.5 MB per tile from L2 instead of 1 MB:
+// the cp.async version measured 22 B/clk/SM of L2 traffic = 54 k cycles per tile (10.6 ms per layer at M = 6.55 M), i.e.
+// it was bound by the L2 stream, not by the tensor pipe.
+// Replaces FF1 (5.4 ms) + four split-K FF2 passes (10.3 ms) per layer.
 #include <stdint.h>
 
 #include "co_common.cuh"
@@ -28,7 +36,9 @@ constexpr int TILE_B = 128 * 32 * 4;                         // one [128 x 32] o
 constexpr int OFF_W = 2 * KB * TILE_B;                       // after x hi / lo
 constexpr int WST = 3;                                       // weight ring stages (hi + lo each): 2 blocks in flight
 constexpr int SMEM_B = OFF_W + WST * 2 * TILE_B;             // 229 376 (x 128 KB + 3 x 32 KB)
-constexpr int THREADS = 288;                                 // warps 0-3 producers, 4-7 epilogue, 8 issuer
+constexpr int THREADS = 320;                                 // warps 0-3 x producers, 4-7 epilogue, 8 issuer, 9 weight loader
+constexpr int CLUSTER = 2;                                   // CTAs sharing every weight block
+constexpr int WBLOCK_FLOATS = 2 * 128 * 32;                  // one pre-tiled block: hi image, lo image (32 KB)
 constexpr uint32_t SBO = 1024, COL_HLO = 256, COL_Y = 384;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -49,6 +59,28 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d), "r"(a_tmem), "l"(b), "r"(IDESC), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at this CTA-relative offset in EVERY CTA of the cluster when all prior MMAs have retired
+__device__ __forceinline__ void commit_multicast(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)((1u << CLUSTER) - 1)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared memory of every CTA in the cluster (same CTA-relative destination and mbarrier)
+__device__ __forceinline__ void bulk_copy_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"((uint16_t)((1u << CLUSTER) - 1)) : "memory");
 }
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -94,7 +126,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 }
 
 struct FfnArgs {
-  const float *x, *w1hi, *w1lo, *b1, *w2hi, *w2lo, *b2, *scale, *shift;  // scale / shift may be null
+  const float *x, *wtiled, *b1, *b2, *scale, *shift;  // wtiled: co_ffn_tile_weights image; scale / shift may be null
   float* out;
   int M, ldx, ldo;
 };
@@ -109,7 +141,8 @@ __device__ __forceinline__ WBlock wblock(int b) {
   return {ff2, j, kb};
 }
 
-__global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, int m_tiles) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
+    ffn_fused_kernel(const FfnArgs g, int m_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sX = smem;           // [kb][hi, lo]
   unsigned char* sW = smem + OFF_W;   // [stage][hi, lo]
@@ -118,8 +151,8 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
   const uint32_t b0 = s32(bars);
   auto XFULL = [&]() { return b0; };                          // producers: x tile in SMEM                (128)
   auto XEMPTY = [&]() { return b0 + 8; };                     // FF1(3) retired: x tile reusable          (commit)
-  auto WFULL = [&](int s) { return b0 + 8 * (2 + s); };       // producers: weight block landed           (128)
-  auto WEMPTY = [&](int s) { return b0 + 8 * (5 + s); };      // its MMAs retired                         (commit)
+  auto WFULL = [&](int s) { return b0 + 8 * (2 + s); };       // weight block landed: 1 arrive + 32 KB of complete_tx
+  auto WEMPTY = [&](int s) { return b0 + 8 * (5 + s); };      // its MMAs retired in BOTH CTAs      (2 multicast commits)
   auto HFULL = [&](int a) { return b0 + 8 * (8 + a); };       // FF1(j) retired -> epilogue               (commit)
   auto HPFULL = [&]() { return b0 + 8 * 10; };                // epilogue: H_hi / H_lo of chunk j written (128)
   auto HFREE = [&]() { return b0 + 8 * 11; };                 // FF2(j) retired: H[j & 1] and H_lo free   (commit)
@@ -134,20 +167,22 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
   if (tid == 0) {
     auto init = [&](uint32_t bar, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); };
     init(XFULL(), 128); init(XEMPTY(), 1); init(HPFULL(), 128); init(HFREE(), 1); init(YFULL(), 1); init(YEMPTY(), 128);
-    for (int s = 0; s < WST; ++s) { init(WFULL(s), 128); init(WEMPTY(s), 1); }
+    for (int s = 0; s < WST; ++s) { init(WFULL(s), 1); init(WEMPTY(s), CLUSTER); }
     for (int s = 0; s < 2; ++s) init(HFULL(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   tc_before();
   __syncthreads();
+  cluster_sync();  // the peer's barriers are initialised before anything can arrive on them
   tc_after();
   const uint32_t tmem = tmem_base_s;
-  const int ntiles = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // both CTAs of a cluster run the same number of tiles (they consume the same weight-block sequence); a tile index
+  // beyond m_tiles is a dummy: every row fails `row < M`, so nothing is loaded or stored for it
+  const int ntiles = (m_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ producers: x tile, then 32 weight blocks per tile
+    // ------------------------------------------------------------------ producers: x tile (fp32 -> tf32 hi / lo split)
     const int r4 = lane >> 3, c8 = lane & 7;
-    uint32_t wb = 0;  // running weight-block counter (ring position / phase)
     for (int t = 0; t < ntiles; ++t) {
       const int m0 = (blockIdx.x + t * gridDim.x) * BM;
       bar_wait(XEMPTY(), (t & 1) ^ 1);
@@ -172,41 +207,6 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
       }
       fence_async();
       bar_arrive(XFULL());
-      // weight blocks: cp.async straight into the swizzled tile (weights are pre-split, no conversion); two blocks of
-      // look-ahead: blocks b + 1 and b + 2 are in flight while block b is waited for and published
-      auto issue = [&](uint32_t k, int b) {
-        const int st = k % WST;
-        bar_wait(WEMPTY(st), ((k / WST) & 1) ^ 1);
-        const WBlock w = wblock(b);
-        const float* hi = w.ff2 ? g.w2hi + (size_t)w.j * 128 + w.kb * 32 : g.w1hi + (size_t)w.j * 128 * 128 + w.kb * 32;
-        const float* lo = w.ff2 ? g.w2lo + (size_t)w.j * 128 + w.kb * 32 : g.w1lo + (size_t)w.j * 128 * 128 + w.kb * 32;
-        const int ld = w.ff2 ? HID : 128;  // W2 [128, 512]: row = output unit; W1_j [128, 128]: row = hidden unit
-        const uint32_t dhi = s32(sW + (2 * st) * TILE_B), dlo = dhi + TILE_B;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = 16 * i + 4 * warp + r4;
-          const uint32_t soff = (n >> 3) * SBO + (n & 7) * 128 + ((c8 ^ (n & 7)) << 4);
-          cp_async16(dhi + soff, hi + (size_t)n * ld + c8 * 4);
-          cp_async16(dlo + soff, lo + (size_t)n * ld + c8 * 4);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      issue(wb, 0);
-      issue(wb + 1, 1);
-      for (int b = 0; b < 32; ++b) {
-        // publish block b BEFORE reserving a stage for block b + 2: `issue` blocks until the MMAs of block b - 1 have
-        // retired, and a landed block must not wait behind that (measured: with the reservation first the tensor pipe
-        // idled between blocks, 31 % active)
-        if (b + 1 < 32) {
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        fence_async();
-        bar_arrive(WFULL(wb % WST));
-        if (b + 2 < 32) issue(wb + 2, b + 2);
-        ++wb;
-      }
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
             mma_ts(d, a_tmem + col, desc(blo + off), 1);
           }
         }
-        commit(WEMPTY(st));
+        commit_multicast(WEMPTY(st));  // frees the stage in BOTH CTAs' rings (each waits for two arrivals)
         ++wb;
       };
       auto ff1 = [&](uint32_t c) {  // c = global chunk counter; accumulator H[c & 1]
@@ -266,9 +266,26 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
       }
     }
     __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ weight loader: one thread, TMA bulk copies
+    if (lane == 0) {
+      const uint32_t rank = cluster_ctarank();
+      uint32_t wb = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        for (int b = 0; b < 32; ++b, ++wb) {
+          const int st = wb % WST;
+          bar_wait(WEMPTY(st), ((wb / WST) & 1) ^ 1);   // the stage is free in both CTAs
+          bar_expect_tx(WFULL(st), 2 * TILE_B);           // own piece + the peer's piece will land here
+          // piece `rank` (0 = hi image, 1 = lo image) of block b -> the same ring slot of every CTA in the cluster
+          bulk_copy_multicast(s32(sW + (2 * st + rank) * TILE_B), g.wtiled + (size_t)b * WBLOCK_FLOATS + rank * (TILE_B / 4),
+                              TILE_B, WFULL(st));
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps 4..7: one row per thread
-    const int q4 = warp & 3, row_in_tile = 32 * q4 + lane;
+    const int q4 = warp & 3, row_in_tile = 32 * q4 + lane;  // (warps 4..7: TMEM lane quarter = warp % 4)
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q4) << 16);
     uint32_t c = 0;
     uint32_t r[32];
@@ -328,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
   }
   tc_before();
   __syncthreads();
+  cluster_sync();  // no CTA leaves while its peer may still multicast into its shared memory / arrive on its barriers
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
@@ -336,10 +354,41 @@ __global__ void __launch_bounds__(THREADS, 1) ffn_fused_kernel(const FfnArgs g, 
 
 using namespace co;
 
-extern "C" int co_ffn_fused(const float* x, const float* w1hi, const float* w1lo, const float* b1, const float* w2hi,
-                                  const float* w2lo, const float* b2, const float* scale, const float* shift, float* out,
-                                  int M, int ldx, int ldo, void* stream) {
-  if (!x || !w1hi || !w1lo || !b1 || !w2hi || !w2lo || !b2 || !out) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: null pointer%s");
+namespace co {
+namespace ffn {
+// Pre-tile W1 [512,128] / W2 [128,512] (hi and lo parts) into the shared-memory image the kernel streams: 32 blocks in
+// issue order, each = hi image then lo image of a [128 x 32] K-major SWIZZLE_128B operand tile (16 KB each).
+__global__ void __launch_bounds__(256) tile_weights_kernel(const float* __restrict__ w1hi, const float* __restrict__ w1lo,
+                                                            const float* __restrict__ w2hi, const float* __restrict__ w2lo,
+                                                            float* __restrict__ out) {
+  const int b = blockIdx.x;  // block 0..31
+  const WBlock w = wblock(b);
+  for (int idx = threadIdx.x; idx < 128 * 32; idx += blockDim.x) {
+    const int n = idx >> 5, c = idx & 31;
+    const size_t src = w.ff2 ? (size_t)n * HID + w.j * 128 + w.kb * 32 + c          // W2[n][j*128 + kb*32 + c]
+                             : ((size_t)w.j * 128 + n) * 128 + w.kb * 32 + c;       // W1[j*128 + n][kb*32 + c]
+    const uint32_t off = ((n >> 3) * SBO + (n & 7) * 128 + ((((c >> 2) ^ (n & 7))) << 4) + (c & 3) * 4) >> 2;
+    out[(size_t)b * WBLOCK_FLOATS + off] = w.ff2 ? w2hi[src] : w1hi[src];
+    out[(size_t)b * WBLOCK_FLOATS + TILE_B / 4 + off] = w.ff2 ? w2lo[src] : w1lo[src];
+  }
+}
+}  // namespace ffn
+}  // namespace co
+
+extern "C" long co_ffn_tiled_weight_floats(void) { return 32L * co::ffn::WBLOCK_FLOATS; }
+
+extern "C" int co_ffn_tile_weights(const float* w1hi, const float* w1lo, const float* w2hi, const float* w2lo, float* wtiled,
+                                   void* stream) {
+  if (!w1hi || !w1lo || !w2hi || !w2lo || !wtiled) return fail(CO_ERR_BAD_ARG, "co_ffn_tile_weights: null pointer%s");
+  if ((uintptr_t)wtiled & 127) return fail(CO_ERR_BAD_ARG, "co_ffn_tile_weights: output must be 128-byte aligned%s");
+  co::ffn::tile_weights_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(w1hi, w1lo, w2hi, w2lo, wtiled);
+  return check_launch("co_ffn_tile_weights");
+}
+
+extern "C" int co_ffn_fused(const float* x, const float* wtiled, const float* b1, const float* b2, const float* scale,
+                            const float* shift, float* out, int M, int ldx, int ldo, void* stream) {
+  if (!x || !wtiled || !b1 || !b2 || !out) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: null pointer%s");
+  if ((uintptr_t)wtiled & 127) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: wtiled must be 128-byte aligned%s");
   if ((scale == nullptr) != (shift == nullptr)) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: scale and shift go together%s");
   if (M < 0 || ldx < 128 || ldo < 128 || (ldx & 3) || (ldo & 3)) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: bad shape%s");
   if (M == 0) return CO_OK;
@@ -351,9 +400,10 @@ extern "C" int co_ffn_fused(const float* x, const float* w1hi, const float* w1lo
     configured = true;
   }
   const int m_tiles = (M + ffn::BM - 1) / ffn::BM;
-  int grid = device_info().sm_count;
-  if (grid > m_tiles) grid = m_tiles;
-  ffn::FfnArgs g{x, w1hi, w1lo, b1, w2hi, w2lo, b2, scale, shift, out, M, ldx, ldo};
+  int grid = device_info().sm_count & ~(ffn::CLUSTER - 1);  // whole clusters (148 = 74 x 2)
+  const int need = (m_tiles + ffn::CLUSTER - 1) & ~(ffn::CLUSTER - 1);
+  if (grid > need) grid = need;
+  ffn::FfnArgs g{x, wtiled, b1, b2, scale, shift, out, M, ldx, ldo};
   ffn::ffn_fused_kernel<<<grid, ffn::THREADS, ffn::SMEM_B, (cudaStream_t)stream>>>(g, m_tiles);
   return check_launch("co_ffn_fused");
 }

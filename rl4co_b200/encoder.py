@@ -167,6 +167,20 @@ class AttentionModelEncoder(nn.Module):
             cache[key] = hit
         return hit[1]
 
+    def _ffn_tiled(self, w1, w2):
+        """Pre-tiled (TMA-ready) image of an FFN block's split weights, cached until either parameter is modified."""
+        from . import native
+
+        cache = self.__dict__.setdefault("_ffn_cache", {})
+        key = (id(w1), id(w2))
+        ver = (w1._version, w1.data_ptr(), w2._version, w2.data_ptr())
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            s1, s2 = self._split(w1), self._split(w2)
+            hit = (ver, native.ffn_tile_weights(s1[0], s1[1], s2[0], s2[1]))
+            cache[key] = hit
+        return hit[1]
+
     def _linear_splitk(self, x, lin, residual, aff):
         """out = affine(x @ W^T + b + residual) for K = k*128 through the W-stationary K=128 pipeline:
         k passes, each accumulating onto the previous partial via the epilogue's residual operand."""
@@ -230,8 +244,7 @@ class AttentionModelEncoder(nn.Module):
             if self._ffn_fusable(ffn):
                 # FF1 -> ReLU -> FF2 (+ skip, + folded BatchNorm) in one kernel: the [B*N, 512] hidden activation
                 # stays in tensor memory (co_ffn_fused); CO_FFN=split forces the separate GEMMs
-                w1, w2 = self._split(lins[0].weight), self._split(lins[1].weight)
-                h = native.ffn_fused(h, w1[0], w1[1], lins[0].bias, w2[0], w2[1], lins[1].bias,
+                h = native.ffn_fused(h, self._ffn_tiled(lins[0].weight, lins[1].weight), lins[0].bias, lins[1].bias,
                                      scale=aff[0] if aff is not None else None, shift=aff[1] if aff is not None else None)
                 if aff is None:
                     h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()

@@ -39,7 +39,7 @@ EXPORTS = [
     "co_version", "co_last_error_string", "co_device_sm_count", "co_tsp_step", "co_cvrp_action_mask",
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
-    "co_ffn_fused", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
+    "co_ffn_fused", "co_ffn_tile_weights", "co_ffn_tiled_weight_floats", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
     "co_sdvrp_step", "co_sdvrp_action_mask",
 ]
 
@@ -138,7 +138,9 @@ def lib() -> ctypes.CDLL:
     L.co_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]
     L.co_gemm_tf32x3.argtypes = [c_void_p] * 8 + [c_int] * 7 + [c_void_p]
     L.co_encoder_mha.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
-    L.co_ffn_fused.argtypes = [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]
+    L.co_ffn_fused.argtypes = [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]
+    L.co_ffn_tile_weights.argtypes = [c_void_p] * 5 + [c_void_p]
+    L.co_ffn_tiled_weight_floats.restype = ctypes.c_long
     L.co_generate_uniform.argtypes = [c_void_p, ctypes.c_long, c_uint64, c_uint64, c_float, c_float, c_void_p]
     L.co_generate_demand.argtypes = [c_void_p, ctypes.c_long, c_uint64, c_uint64, c_int, c_int, c_float, c_void_p]
     L.co_dihedral8.argtypes = [c_void_p, c_void_p, ctypes.c_long, c_int, c_void_p]
@@ -361,18 +363,26 @@ def encoder_mha(qkv, B, N):
 
 
 @_on_device_of_first_tensor
-def ffn_fused(x, w1_hi, w1_lo, b1, w2_hi, w2_lo, b2, scale=None, shift=None, out=None):
+def ffn_tile_weights(w1_hi, w1_lo, w2_hi, w2_lo):
+    """Pre-tile the split FFN weights (W1 [512,128], W2 [128,512]) into the image `ffn_fused` streams with TMA."""
+    if tuple(w1_hi.shape) != (4 * EMBED_DIM, EMBED_DIM) or tuple(w2_hi.shape) != (EMBED_DIM, 4 * EMBED_DIM):
+        raise ValueError("co_ffn_fused is instantiated for a 128 -> 512 -> 128 feed-forward block")
+    out = torch.empty(lib().co_ffn_tiled_weight_floats(), dtype=F32, device=w1_hi.device)
+    _check(lib().co_ffn_tile_weights(_ptr(w1_hi, F32, "w1_hi"), _ptr(w1_lo, F32, "w1_lo"), _ptr(w2_hi, F32, "w2_hi"),
+                                     _ptr(w2_lo, F32, "w2_lo"), _ptr(out, F32, "wtiled"), _stream()), "co_ffn_tile_weights")
+    return out
+
+
+@_on_device_of_first_tensor
+def ffn_fused(x, wtiled, b1, b2, scale=None, shift=None, out=None):
     """out = ((x + relu(x W1^T + b1) W2^T + b2)) * scale + shift in one kernel (co_ffn_fused); x [M, 128] with
-    row stride % 4 == 0, W1 [512, 128], W2 [128, 512] pre-split by `split_tf32`."""
+    row stride % 4 == 0, `wtiled` from `ffn_tile_weights`."""
     M = x.shape[0]
     if x.dim() != 2 or x.shape[1] != EMBED_DIM or x.stride(1) != 1:
         raise ValueError(f"x must be [M, {EMBED_DIM}] with unit inner stride, got {tuple(x.shape)}")
-    if tuple(w1_hi.shape) != (4 * EMBED_DIM, EMBED_DIM) or tuple(w2_hi.shape) != (EMBED_DIM, 4 * EMBED_DIM):
-        raise ValueError("co_ffn_fused is instantiated for a 128 -> 512 -> 128 feed-forward block")
     if out is None:
         out = torch.empty(M, EMBED_DIM, dtype=F32, device=x.device)
-    _check(lib().co_ffn_fused(_ptr(x, F32, "x", True), _ptr(w1_hi, F32, "w1_hi"), _ptr(w1_lo, F32, "w1_lo"),
-                              _ptr(b1, F32, "b1"), _ptr(w2_hi, F32, "w2_hi"), _ptr(w2_lo, F32, "w2_lo"),
+    _check(lib().co_ffn_fused(_ptr(x, F32, "x", True), _ptr(wtiled, F32, "wtiled"), _ptr(b1, F32, "b1"),
                               _ptr(b2, F32, "b2"), _ptr(scale, F32, "scale"), _ptr(shift, F32, "shift"),
                               _ptr(out, F32, "out", True), M, x.stride(0), out.stride(0), _stream()), "co_ffn_fused")
     return out

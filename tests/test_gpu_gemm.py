@@ -87,7 +87,7 @@ def test_ffn_fused_vs_float64(M, affine):
     scale = (1 + 0.2 * torch.randn(128, device=dev)) if affine else None
     shift = (0.1 * torch.randn(128, device=dev)) if affine else None
     w1s, w2s = native.split_tf32(w1), native.split_tf32(w2)
-    out = native.ffn_fused(x, w1s[0], w1s[1], b1, w2s[0], w2s[1], b2, scale, shift)
+    out = native.ffn_fused(x, native.ffn_tile_weights(w1s[0], w1s[1], w2s[0], w2s[1]), b1, b2, scale, shift)
     xd = x.double()
     ref = xd + torch.relu(xd @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
     if affine:

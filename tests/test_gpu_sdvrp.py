@@ -89,7 +89,8 @@ def test_sdvrp_decoder_step_vs_reference_logits(golden, name):
 
 @pytest.mark.parametrize("name", ["am_sdvrp20", "am_sdvrp50"])
 @pytest.mark.parametrize("mode", ["greedy", "sampling", "evaluate"])
-def test_sdvrp_policy_vs_golden(golden, name, mode):
+def test_sdvrp_policy_vs_golden(golden, name, mode, monkeypatch):
+    from rl4co_b200 import decoding
     from rl4co_b200.envs import get_env
     from rl4co_b200.tensordict import TensorDict
 
@@ -101,8 +102,10 @@ def test_sdvrp_policy_vs_golden(golden, name, mode):
     td = env.reset(TensorDict(inst, batch_size=[B]))
     pol.encoder = _FixedEncoder(g["h"].to(DEV))
     kw = {}
-    if mode == "sampling":
-        kw = dict(decode_type="sampling", noise=g["sampling_noise"].to(DEV))
+    if mode == "sampling":  # recorded-noise protocol: serve the Exp(1) draws torch.multinomial consumed, one per step
+        served = iter(g["sampling_noise"].to(DEV).unbind(0))
+        monkeypatch.setattr(decoding.Sampling, "_noise", lambda self, logits: next(served).contiguous())
+        kw = dict(decode_type="sampling")
     elif mode == "evaluate":
         kw = dict(actions=g["eval_actions"].to(DEV))
     else:
