@@ -115,6 +115,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -295,23 +315,45 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
         bar_wait(HFULL(c & 1), (c >> 1) & 1);
         tc_after();
         const uint32_t hcol = lane_base + (c & 1) * 128;
-        for (int cc = 0; cc < 4; ++cc) {
-          tmem_ld32(hcol + cc * 32, r);
-          // H_lo is single-buffered: FF2 of the previous chunk must have retired before it is overwritten
-          if (cc == 0 && c >= 1) bar_wait(HFREE(), (c - 1) & 1);
+        // 32 columns at a time; the TMEM load of the next 32 columns is in flight while the current ones are processed
+        // (bias + ReLU + tf32 split).  The bias comes in 16-byte uniform loads (it was one LDG per element: 128 per
+        // thread and chunk, which made this epilogue -- not the MMAs -- the pacing stage of the kernel).
+        auto process = [&](const uint32_t (&rr)[32], int cc) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float hi[16], lo[16];
+            const float4* bp = reinterpret_cast<const float4*>(g.b1 + j * 128 + cc * 32 + 16 * half);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float v = fmaxf(__uint_as_float(r[16 * half + i]) + __ldg(g.b1 + j * 128 + cc * 32 + 16 * half + i), 0.f);
-              hi[i] = rna(v);
-              lo[i] = v - hi[i];
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = __ldg(bp + q);
+              const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * q + e;
+                const float v = fmaxf(__uint_as_float(rr[16 * half + i]) + bb[e], 0.f);
+                hi[i] = rna(v);
+                lo[i] = v - hi[i];
+              }
             }
             tmem_st16(hcol + cc * 32 + 16 * half, hi);
             tmem_st16(lane_base + COL_HLO + cc * 32 + 16 * half, lo);
           }
-        }
+        };
+        uint32_t r2[32];
+        tmem_ld32_issue(hcol, r);
+        tmem_ld_wait(r);
+        // H_lo is single-buffered: FF2 of the previous chunk must have retired before it is overwritten
+        if (c >= 1) bar_wait(HFREE(), (c - 1) & 1);
+        tmem_ld32_issue(hcol + 32, r2);
+        process(r, 0);
+        tmem_ld_wait(r2);
+        tmem_ld32_issue(hcol + 64, r);
+        process(r2, 1);
+        tmem_ld_wait(r);
+        tmem_ld32_issue(hcol + 96, r2);
+        process(r, 2);
+        tmem_ld_wait(r2);
+        process(r2, 3);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_before();
         bar_arrive(HPFULL());
@@ -329,11 +371,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
             const float4 xv = __ldg(xr + q);
             float y[4] = {__uint_as_float(r[4 * q]) + xv.x, __uint_as_float(r[4 * q + 1]) + xv.y,
                           __uint_as_float(r[4 * q + 2]) + xv.z, __uint_as_float(r[4 * q + 3]) + xv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = cc * 32 + 4 * q + e;
-              y[e] += __ldg(g.b2 + col);
-              if (g.scale) y[e] = fmaf(y[e], __ldg(g.scale + col), __ldg(g.shift + col));
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(g.b2 + cc * 32) + q);  // uniform 16-byte loads
+            y[0] += bq.x; y[1] += bq.y; y[2] += bq.z; y[3] += bq.w;
+            if (g.scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(g.scale + cc * 32) + q);
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(g.shift + cc * 32) + q);
+              y[0] = fmaf(y[0], sc.x, sh.x); y[1] = fmaf(y[1], sc.y, sh.y);
+              y[2] = fmaf(y[2], sc.z, sh.z); y[3] = fmaf(y[3], sc.w, sh.w);
             }
             dst[q] = make_float4(y[0], y[1], y[2], y[3]);
           }
@@ -389,6 +433,8 @@ extern "C" int co_ffn_fused(const float* x, const float* wtiled, const float* b1
                             const float* shift, float* out, int M, int ldx, int ldo, void* stream) {
   if (!x || !wtiled || !b1 || !b2 || !out) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: null pointer%s");
   if ((uintptr_t)wtiled & 127) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: wtiled must be 128-byte aligned%s");
+  if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)scale | (uintptr_t)shift) & 15)
+    return fail(CO_ERR_BAD_ARG, "co_ffn_fused: pointers must be 16-byte aligned%s");
   if ((scale == nullptr) != (shift == nullptr)) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: scale and shift go together%s");
   if (M < 0 || ldx < 128 || ldo < 128 || (ldx & 3) || (ldo & 3)) return fail(CO_ERR_BAD_ARG, "co_ffn_fused: bad shape%s");
   if (M == 0) return CO_OK;
