@@ -209,6 +209,9 @@ typedef struct co_rollout_args {
   int32_t cache_width;       /* floats per row of `cache`: 4E, or 5E = tsp layout with   */
                              /* the first-node table; 0 = co_cache_width(env_kind)       */
   int32_t reserved0;
+  /* sdvrp: dynamic-embedding weights [wk | wv | W_out^T wl] = SDVRPDynamicEmbedding.projection.weight[:, 0] with
+   * the logit third folded like block 2 of the cache (nn/env_embeddings/dynamic.py:60-78); NULL otherwise */
+  const float* dyn_w;        /* [3E] */
 } co_rollout_args;
 
 int co_cache_width(int env_kind); /* floats per node row of the widest rollout cache layout (tsp 5E, cvrp 4E) */

@@ -32,6 +32,7 @@ DST_ROOT = os.path.join(HERE, "_ref")
 #: hot-path files of the reference + the next-row files of 8f whose parity tests use them
 FILES = [
     "rl4co/data/dataset.py",
+    "rl4co/data/generate_data.py",
     "rl4co/data/transforms.py",
     "rl4co/data/utils.py",
     "rl4co/envs/common/base.py",

@@ -70,6 +70,11 @@ struct Smem {
   unsigned char order[32 * SPL];    // cvrp: customers sorted by demand (ascending)
   unsigned char rank_of[32 * SPL];  // cvrp: demand rank of each customer (inverse of `order`)
   float ll_acc;
+  // sdvrp (dynamic embedding, nn/env_embeddings/dynamic.py:60-78): the remaining demand d_n adds d_n * w to node n's
+  // glimpse key / value / folded logit key; everything the step needs beyond d_n is a per-node or per-step scalar
+  float wdyn[3 * E];                // [wk | wv | W_out^T wl]
+  float pwk[32 * SPL * 8 + 8];      // ptab[n] . wk_h per (node, head); last 8 = the zero row
+  float ol[8];                      // per-head o_h . wl'_h of the current step
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -114,8 +119,9 @@ static __device__ __noinline__ void first_node_gemv(const float* __restrict__ w_
 template <int ENV>
 __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used, float thr, int cur, bool anyfeas) {
   if (ENV == CO_ENV_TSP) return !visbit;
-  // cvrp/env.py:126-136
+  // cvrp/env.py:126-136, sdvrp/env.py:110-116 (depot rule shared)
   if (n == 0) return !(cur == 0 && anyfeas);
+  if (ENV == CO_ENV_SDVRP) return !visbit && !(d == 0.0f) && !(used >= thr);  // thr = capacity here; visbit = padding
   return !visbit && !((d + used) > thr);
 }
 
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
   constexpr int CW = CWB * E;        // cache row width: 4E, or 5E (tsp with the first-node table)
   constexpr int CUR_BLK = CWB - 1;   // block holding the current-node table (always the last one)
   constexpr bool first_table = (ENV == CO_ENV_TSP) && (CWB == 5);
+  constexpr bool VRP = (ENV != CO_ENV_TSP);        // depot env with capacity context (cvrp, sdvrp)
+  constexpr bool SD = (ENV == CO_ENV_SDVRP);       // split deliveries: dynamic demand + dynamic embedding
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<SPL>& sm = *reinterpret_cast<Smem<SPL>*>(smem_raw);
@@ -183,15 +191,31 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     }
     if (tid < E) {
       sm.ptab[NS * E + tid] = 0.f;
-      sm.wcap[tid] = (ENV == CO_ENV_CVRP) ? A.w_capacity[tid] : 0.f;
+      sm.wcap[tid] = VRP ? A.w_capacity[tid] : 0.f;
     }
     if (tid < NS) {
       sm.loc[tid] = (tid < N) ? reinterpret_cast<const float2*>(A.locs)[(size_t)b * N + tid] : make_float2(0.f, 0.f);
-      sm.dem[tid] = (ENV == CO_ENV_CVRP && tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
+      sm.dem[tid] = (VRP && tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
     }
-    const float cap = (ENV == CO_ENV_CVRP && A.vehicle_capacity) ? A.vehicle_capacity[b] : 1.0f;
-    const float thr = cap + 1e-5f;  // fp32 add, as `td["vehicle_capacity"] + 1e-5`
+    if (SD) {
+      for (int i = tid; i < 3 * E; i += 256) sm.wdyn[i] = A.dyn_w[i];
+    }
+    const float cap = (VRP && A.vehicle_capacity) ? A.vehicle_capacity[b] : 1.0f;
+    // cvrp: fp32 add, as `td["vehicle_capacity"] + 1e-5`; sdvrp compares `used >= vehicle_capacity` (no slack)
+    const float thr = SD ? cap : cap + 1e-5f;
     __syncthreads();
+    if (SD) {  // per-(node, head) dot of the context-table row with the dynamic key weight
+      for (int i = tid; i < (NS + 1) * 8; i += 256) {
+        const int n = i >> 3, hh = i & 7;
+        float acc = 0.f;
+        if (n < N) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc = fmaf(sm.ptab[n * E + hh * D + c], sm.wdyn[hh * D + c], acc);
+        }
+        sm.pwk[i] = acc;
+      }
+      __syncthreads();
+    }
     if (ENV == CO_ENV_CVRP) {  // rank-sort customers by demand (ties by index) -> sm.order
       if (tid >= 1 && tid < N) {
         const float d = sm.dem[tid];
@@ -205,10 +229,10 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       __syncthreads();
     }
-    float dmk[SPL];
+    float dmk0[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; ++k) dmk[k] = sm.dem[lane + 32 * k];
-    const float dL = sm.dem[nL];
+    for (int k = 0; k < SPL; ++k) dmk0[k] = sm.dem[lane + 32 * k];
+    const float dL0 = sm.dem[nL];
     // scores split by linearity: q.K = ptab[cur].K + qfix.K + rem * (wcap.K); the last two are
     // per-episode / per-instance constants held in registers (FK, WK)
     auto head_dot = [&](const float* vec, float (&out)[SPL]) {
@@ -241,7 +265,15 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     float WK[SPL], FK[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) { WK[k] = 0.f; FK[k] = 0.f; }
-    if (ENV == CO_ENV_CVRP) head_dot(sm.wcap, WK);
+    if (VRP) head_dot(sm.wcap, WK);
+    // sdvrp per-instance / per-lane constants of the dynamic terms
+    float WKW = 0.f, wv_d = 0.f, wl_d = 0.f;
+    if (SD) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) WKW = fmaf(sm.wcap[h * D + c], sm.wdyn[h * D + c], WKW);  // wcap_h . wk_h
+      wv_d = sm.wdyn[E + h * D + (lane & 15)];
+      wl_d = sm.wdyn[2 * E + h * D + (lane & 15)];
+    }
     if (!(A.flags & CO_ROLLOUT_NO_PREFETCH) && b + (int)gridDim.x < B_inst) {  // next instance's cache rows -> L2
       const char* nxt = reinterpret_cast<const char*>(A.cache + (size_t)(b + gridDim.x) * N * CW);
       const int lines = (N * CW * 4 + 127) >> 7;
@@ -270,6 +302,13 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       float used = 0.f, dist = 0.f;
       bool anyfeas = false, done = false, depot_seen = false;
+      // (remaining) demand of this thread's glimpse nodes / logits node: constant for cvrp, dynamic for sdvrp
+      float dmk[SPL], dL = dL0;
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) dmk[k] = dmk0[k];
+      int nrem = 0;                 // sdvrp: customers with demand left
+      int pend_a = -1;              // sdvrp: demand write-back deferred past the next barrier (see env_step)
+      float pend_d = 0.f, FKW = 0.f;
       __syncthreads();  // previous trajectory finished with qfix / ll_acc
       if (tid < E) {
         float g = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;
@@ -280,16 +319,31 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 
       // one environment transition, replicated in every thread
       auto env_step = [&](int a) {
+        if (!SD) {  // (sdvrp: nodes may be revisited; mybits only flags the padding slots there)
 #pragma unroll
-        for (int k = 0; k < SPL; ++k) mybits |= (a == lane + 32 * k) ? (1u << k) : 0u;
-        mybits |= (a == nL) ? 0x100u : 0u;
+          for (int k = 0; k < SPL; ++k) mybits |= (a == lane + 32 * k) ? (1u << k) : 0u;
+          mybits |= (a == nL) ? 0x100u : 0u;
+        }
         if (h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
           const float2 pa = sm.loc[a], pp = sm.loc[prev];
           const float dx = pa.x - pp.x, dy = pa.y - pp.y;
-          if (ENV == CO_ENV_CVRP || t != 0) dist += sqrtf(dx * dx + dy * dy);
+          if (VRP || t != 0) dist += sqrtf(dx * dx + dy * dy);
         }
         if (ENV == CO_ENV_TSP) {
           if (t == 0) first = a;
+        } else if (SD) {
+          // sdvrp/env.py:55-82: deliver min(remaining demand, remaining capacity); every thread replays the arithmetic.
+          // sm.dem[a] is read by all threads here, so the owner's write-back waits until after the next block barrier.
+          const float d_a = sm.dem[a];
+          const float delivered = fminf(d_a, cap - used);
+          used = (used + delivered) * (a != 0 ? 1.0f : 0.0f);
+          const float d_new = d_a + (-delivered);  // scatter_add(-1, a, -delivered)
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) dmk[k] = (a == lane + 32 * k) ? d_new : dmk[k];
+          dL = (a == nL) ? d_new : dL;
+          nrem += ((d_new > 0.f) ? 1 : 0) - ((d_a > 0.f) ? 1 : 0);
+          pend_a = a; pend_d = d_new;
+          anyfeas = (nrem > 0) && !(used >= cap);
         } else {
           used = (used + sm.dem[a == 0 ? 1 : a]) * (a != 0 ? 1.0f : 0.0f);  // cvrp/env.py:70-76
           // distinct nodes visited: a customer is new by construction (masked once visited), the depot
@@ -312,11 +366,17 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           anyfeas = (pmin < N - 1) && !((sm.dem[sm.order[pmin < N - 1 ? pmin : 0]] + used) > thr);
         }
         prev = a; cur = a; ++t;
-        done = (ENV == CO_ENV_TSP) ? (t >= N) : (nvis >= N);  // cvrp: all nodes incl. the depot visited
+        // cvrp: all nodes incl. the depot visited; sdvrp: no positive demand left (sdvrp/env.py:71)
+        done = (ENV == CO_ENV_TSP) ? (t >= N) : (SD ? (nrem == 0) : (nvis >= N));
       };
 
+      if (SD) {  // customers with demand: counted by every thread from shared memory (uniform)
+        for (int n = 1; n < N; ++n) nrem += (sm.dem[n] > 0.f) ? 1 : 0;
+        anyfeas = (nrem > 0) && !(used >= cap);
+        done = (nrem == 0);
+      }
       if (forced_start) {  // multistart pre_decoder_hook, decoding.py:309-326 + ops.py:128-149
-        const int a0 = (s % A.num_loc) + (ENV == CO_ENV_CVRP ? 1 : 0);
+        const int a0 = (s % A.num_loc) + (VRP ? 1 : 0);
         if (tid == 0) { act_row[0] = a0; lp_row[0] = 0.f; }
         env_step(a0);
         if (ENV == CO_ENV_TSP) {
@@ -328,6 +388,10 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       __syncthreads();
       head_dot(sm.qfix, FK);
+      if (SD) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) FKW = fmaf(sm.qfix[h * D + c], sm.wdyn[h * D + c], FKW);  // qfix_h . wk_h
+      }
 
       while (!done && t < T_max) {
         // early, latency-tolerant loads for this step
@@ -359,23 +423,27 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           // scores in log2 units: s * (1/sqrt(head_dim)) * log2(e)
           float sc[SPL], m = -INFINITY;
           bool fz[SPL];
+          // sdvrp: q_h . wk_h = ptab[cur]_h . wk_h + qfix_h . wk_h + rem * (wcap_h . wk_h)
+          const float qwk = SD ? fmaf(rem, WKW, sm.pwk[cur * 8 + h] + FKW) : 0.f;
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
             fz[k] = feasible<ENV>(lane + 32 * k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
             float dot = (sc2[k].x + sc2[k].y) + FK[k];
-            if (ENV == CO_ENV_CVRP) dot = fmaf(rem, WK[k], dot);
+            if (VRP) dot = fmaf(rem, WK[k], dot);
+            if (SD) dot = fmaf(dmk[k], qwk, dot);  // q . (K[n] + d_n wk) = q.K[n] + d_n (q.wk)
             sc[k] = fz[k] ? dot * (0.25f * LOG2E) : -INFINITY;
             m = fmaxf(m, sc[k]);
           }
           m = funkey(__reduce_max_sync(FULL, fkey(m)));
           float2 acc[8];
-          float esum = 0.f;
+          float esum = 0.f, sed = 0.f;  // sed (sdvrp) = sum_n e_n d_n: the dynamic value term is sed * wv_h
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
             const float e = fz[k] ? ex2(sc[k] - m) : 0.f;
             esum += e;
+            if (SD) sed = fmaf(e, dmk[k], sed);
             const float2 e2 = make_float2(e, e);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = ffma2(e2, Vr[k][j], acc[j]);
@@ -385,6 +453,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 #pragma unroll
           for (int c = 0; c < 4; ++c) trow[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
           esum = warp_sum(esum);
+          if (SD) sed = warp_sum(sed);
           __syncwarp();
           const int d = lane & 15, half = lane >> 4;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -397,14 +466,26 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           }
           float r = (s0 + s1) + (s2 + s3);
           r += __shfl_xor_sync(FULL, r, 16);
+          if (SD) r = fmaf(sed, wv_d, r);  // + (sum_n e_n d_n) * wv_h[d]
+          const float ov = __fdividef(r, esum);
           if (lane < 16) {
             const int e = h * D + d;
-            sm.o[e + 4 * (e / EPP)] = __fdividef(r, esum);
+            sm.o[e + 4 * (e / EPP)] = ov;
+          }
+          if (SD) {  // o_h . wl'_h for the dynamic logit term (16 lanes hold the head's 16 channels)
+            float t4 = ov * wl_d;
+            t4 += __shfl_xor_sync(FULL, t4, 8);
+            t4 += __shfl_xor_sync(FULL, t4, 4);
+            t4 += __shfl_xor_sync(FULL, t4, 2);
+            t4 += __shfl_xor_sync(FULL, t4, 1);
+            if (lane == 0) sm.ol[h] = t4;
           }
         }
         __syncthreads();  // B1: heads complete
 
         // ---------------- pointer logits + tanh clip + mask: thread (nL, part)
+        if (SD && tid == 0 && pend_a >= 0) sm.dem[pend_a] = pend_d;  // deferred demand write-back (every thread is
+                                                                     // past the env_step that read the old value)
         const bool fzL = feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
         float z;
         {
@@ -421,6 +502,10 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           float p = ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
 #pragma unroll
           for (int off = PARTS / 2; off > 0; off >>= 1) p += __shfl_xor_sync(FULL, p, off);
+          if (SD) {  // + d_n * (o . wl'): the dynamic logit-key term, heads summed in fixed order
+            const float4 u0 = reinterpret_cast<const float4*>(sm.ol)[0], u1 = reinterpret_cast<const float4*>(sm.ol)[1];
+            p = fmaf(dL, ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w)), p);
+          }
           const float lg = tanhf(p * 0.08838834764831845f) * clip;  // /sqrt(E), tanh clip (decoding.py:169-170)
           z = fzL ? lg * inv_temp : -INFINITY;                       // mask, temperature (decoding.py:173-177)
         }

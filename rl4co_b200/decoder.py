@@ -84,6 +84,7 @@ class FusedPrecomputedCache:
     q_placeholder: torch.Tensor | None  # [E] tsp
     w_capacity: torch.Tensor | None     # [E] cvrp
     w_first: torch.Tensor | None = None  # [E, E] tsp: project_context.weight[:, :E] (first-node GEMV operand)
+    dyn_w: torch.Tensor | None = None    # [3E] sdvrp: dynamic-embedding weights [wk | wv | W_out^T wl]
     _logit_weight: torch.Tensor | None = None
     _logit_key: torch.Tensor | None = None
 
@@ -209,8 +210,15 @@ class FusedAttentionModelDecoder(nn.Module):
             w_cap = wc[:, E].contiguous()
         return FusedPrecomputedCache(
             node_embeddings=embeddings, graph_context=graph_context, rollout_cache=cache, q_placeholder=q_ph,
-            w_capacity=w_cap, w_first=w_first, _logit_weight=self.project_node_embeddings.weight[2 * E:],
+            w_capacity=w_cap, w_first=w_first, dyn_w=self._dynamic_weights() if self.is_dynamic_embedding else None,
+            _logit_weight=self.project_node_embeddings.weight[2 * E:],
         )
+
+    def _dynamic_weights(self) -> torch.Tensor:
+        """[wk | wv | W_out^T wl]: SDVRPDynamicEmbedding.projection.weight[:, 0] with the logit third folded with
+        pointer.project_out like block 2 of the cache (logits = heads . (L + d wl) W_out-folded)."""
+        wd = self.dynamic_embedding.projection.weight.detach()[:, 0]
+        return torch.cat((wd[:2 * E], self.pointer.project_out.weight.detach().t() @ wd[2 * E:])).contiguous()
 
     def pre_decoder_hook(self, td, env, embeddings, num_starts: int = 0):
         """am/decoder.py:195-199"""
@@ -229,8 +237,7 @@ class FusedAttentionModelDecoder(nn.Module):
         w.project_out_t = None  # logit key is folded
         if self.is_dynamic_embedding:
             # [wk | wv | W_out^T wl]: the logit third folded like the logit key itself (module docstring, block 2)
-            wd = self.dynamic_embedding.projection.weight.detach()[:, 0]
-            wdyn = torch.cat((wd[:2 * E], self.pointer.project_out.weight.detach().t() @ wd[2 * E:])).contiguous()
+            wdyn = self._dynamic_weights()
             keep.append(wdyn)
             w.dynamic_w = wdyn.data_ptr()
         w._keepalive = keep

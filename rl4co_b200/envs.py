@@ -117,8 +117,16 @@ class FusedEnvBase:
     batch_locked = False
 
     def __init__(self, *, check_solution: bool = True, seed: int | None = None, device: str = "cpu",
-                 batch_size=None, inplace: bool = False, **kwargs):
+                 batch_size=None, inplace: bool = False, data_dir: str = "data/", train_file: str | None = None,
+                 val_file: str | None = None, test_file: str | None = None, **kwargs):
         kwargs.pop("name", None)
+        # rl4co/envs/common/base.py:45-79: optional dataset files per phase, relative to data_dir
+        import os
+
+        self.data_dir = data_dir
+        self.train_file = os.path.join(data_dir, train_file) if train_file is not None else None
+        self.val_file = os.path.join(data_dir, val_file) if val_file is not None else None
+        self.test_file = os.path.join(data_dir, test_file) if test_file is not None else None
         self.check_solution = check_solution
         self.device = torch.device(device)
         self.batch_size = torch.Size([]) if batch_size is None else torch.Size(batch_size)
@@ -172,10 +180,19 @@ class FusedEnvBase:
         return select_start_nodes(td, self, num_starts)
 
     def dataset(self, batch_size=[], phase="train", filename=None):
-        """rl4co/envs/common/base.py:234-268 (generated data or .npz file)."""
+        """rl4co/envs/common/base.py:234-268: the phase's file (`{phase}_file`, or `filename`) when set -- e.g. the
+        seeded validation / test sets of data.generate_default_datasets -- else freshly generated instances; a
+        missing file falls back to generation like the reference."""
         from .data import TensorDictDataset
 
-        td = self.generator(batch_size) if filename is None else self.load_data(filename, batch_size)
+        f = getattr(self, f"{phase}_file", None) if filename is None else filename
+        if f is None:
+            td = self.generator(batch_size)
+        else:
+            try:
+                td = self.load_data(f, batch_size)
+            except FileNotFoundError:
+                td = self.generator(batch_size)
         return TensorDictDataset(td)
 
     @staticmethod

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "gemm_tf32x3.cu",
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
            "ffn_fused.cu", "data_kernels.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
@@ -30,7 +30,7 @@ ENV_TSP, ENV_CVRP = 0, 1
 ENV_SDVRP = 2
 ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP}
 #: environments the whole-episode kernel (co_rollout) is instantiated for; others take the stepping kernels
-ROLLOUT_ENVS = ("tsp", "cvrp")
+ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp")
 SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
 ROLLOUT_FORCED_START = 1
 EMBED_DIM, NUM_HEADS = 128, 8
@@ -64,6 +64,7 @@ class RolloutArgs(Structure):
         ("actions_out", c_void_p), ("logp_out", c_void_p), ("reward_out", c_void_p), ("loglik_out", c_void_p),
         ("steps_out", c_void_p), ("max_steps_out", c_void_p), ("used_capacity_out", c_void_p),
         ("node_emb", c_void_p), ("w_first", c_void_p), ("cache_width", c_int32), ("reserved0", c_int32),
+        ("dyn_w", c_void_p),
     ]
 
 
@@ -424,7 +425,7 @@ def reward_stats(reward, out2):
 @_on_device_of_first_tensor
 def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, locs, demand, vehicle_capacity,
             B_inst, N, num_starts=1, forced_start=False, num_loc=0, T_max=None, forced_actions=None, noise=None,
-            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0, node_emb=None, w_first=None):
+            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0, node_emb=None, w_first=None, dyn_w=None):
     """Launch the persistent rollout kernel; returns dict of device tensors (no host sync).
     `cache` is [B_inst, N, W]: W = 4E ([K | V | L' | cur-table]; tsp then needs `node_emb` [B_inst, N, E] and
     `w_first` [E, E] for the per-episode first-node GEMV) or, tsp only, 5E (with the first-node table)."""
@@ -432,14 +433,14 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
     S = max(1, int(num_starts))
     B_traj = B_inst * S
     if T_max is None:
-        T_max = N if env_name == "tsp" else 2 * (N - 1)
+        T_max = N if env_name == "tsp" else (2 * (N - 1) if env_name == "cvrp" else 3 * (N - 1) + 2)
     actions = torch.empty(B_traj, T_max, dtype=I64, device=dev)
     logp = torch.empty(B_traj, T_max, dtype=F32, device=dev)
     reward = torch.empty(B_traj, dtype=F32, device=dev)
     loglik = torch.empty(B_traj, dtype=F32, device=dev)
     steps = torch.empty(B_traj, dtype=I32, device=dev)
     max_steps = torch.zeros(1, dtype=I32, device=dev)
-    used_out = torch.empty(B_traj, dtype=F32, device=dev) if env_name == "cvrp" else None
+    used_out = torch.empty(B_traj, dtype=F32, device=dev) if env_name in ("cvrp", "sdvrp") else None
     a = RolloutArgs()
     a.env_kind, a.select_mode, a.B_inst, a.num_starts = ENV_KIND[env_name], select_mode, B_inst, S
     a.N, a.T_max, a.num_loc, a.flags = N, T_max, int(num_loc), (ROLLOUT_FORCED_START if forced_start else 0)
@@ -469,6 +470,10 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
             raise ValueError("node_emb must be [B_inst, N, E] and w_first [E, E]")
         a.node_emb, a.w_first = _ptr(node_emb, F32, "node_emb"), _ptr(w_first, F32, "w_first")
     a.cache_width = W
+    if env_name == "sdvrp":
+        if dyn_w is None or tuple(dyn_w.shape) != (3 * EMBED_DIM,):
+            raise ValueError("sdvrp needs dyn_w [3E] (dynamic-embedding weights, logit third folded)")
+        a.dyn_w = _ptr(dyn_w, F32, "dyn_w")
     if forced_actions is not None and tuple(forced_actions.shape) != (B_traj, T_max):
         raise ValueError(f"forced_actions must be [{B_traj}, {T_max}], got {tuple(forced_actions.shape)}")
     if noise is not None and (noise.dim() != 3 or noise.shape[1] != B_traj or noise.shape[2] != N):

@@ -131,7 +131,9 @@ class FusedAttentionModelPolicy(nn.Module):
         elif num_samples is not None and num_samples > 1:
             S = num_samples
         B_traj = B * S
-        T_max = N if env_name == "tsp" else 2 * (N - 1)
+        # decode-step bound: tsp N; cvrp 2(N-1) (every customer + a depot return each); sdvrp 3(N-1)+2 (a customer can
+        # be split once per refill on top of that)
+        T_max = N if env_name == "tsp" else (2 * (N - 1) if env_name == "cvrp" else 3 * (N - 1) + 2)
         # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
         cached = self.decoder._precompute_cache(hidden, first_table=True if S > 1 else None)
 
@@ -158,9 +160,10 @@ class FusedAttentionModelPolicy(nn.Module):
         else:
             raise NotImplementedError(f"decode type {decode_type!r} is outside the fused path")
 
-        demand = td["demand"].contiguous() if env_name == "cvrp" else None
-        vcap = td["vehicle_capacity"].reshape(-1).contiguous() if env_name == "cvrp" else None
-        num_loc = getattr(env.generator, "num_loc", N - (1 if env_name == "cvrp" else 0))
+        vrp = env_name in ("cvrp", "sdvrp")
+        demand = td["demand"].contiguous() if vrp else None
+        vcap = td["vehicle_capacity"].reshape(-1).contiguous() if vrp else None
+        num_loc = getattr(env.generator, "num_loc", N - (1 if vrp else 0))
         with torch.no_grad():
             res = native.rollout(
                 env_name, mode, cached.rollout_cache.detach().contiguous(), cached.graph_context_or_none,
@@ -169,7 +172,7 @@ class FusedAttentionModelPolicy(nn.Module):
                 noise=noise.contiguous() if noise is not None else None, tanh_clipping=tanh_clipping,
                 temperature=temperature, seed=seed or 0, offset=philox_offset or 0,
                 node_emb=hidden.detach().contiguous() if env_name == "tsp" else None,
-                w_first=cached.w_first.detach() if cached.w_first is not None else None)
+                w_first=cached.w_first.detach() if cached.w_first is not None else None, dyn_w=cached.dyn_w)
         if env_name == "tsp":
             T = N
         elif decode_type == "evaluate":
@@ -207,6 +210,11 @@ class FusedAttentionModelPolicy(nn.Module):
     def _check(env, td, actions, S):
         if env.name == "tsp":
             bad = native.check_tours(actions, td["locs"].shape[-2])
+        elif env.name == "sdvrp":  # torch replay on the device (validation path), start-major rows share instances
+            tdx = td if S == 1 else TensorDict({k: td[k].repeat(S, *([1] * (td[k].dim() - 1))) for k in ("demand", "vehicle_capacity")},
+                                               batch_size=[td.batch_size[0] * S])
+            env.check_solution_validity(tdx, actions)
+            return
         else:
             bad = native.check_tours(actions, td["locs"].shape[-2], td["demand"].contiguous(),
                                      td["vehicle_capacity"].reshape(-1).contiguous(), B_inst=td["demand"].shape[0])

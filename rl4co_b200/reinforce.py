@@ -168,31 +168,163 @@ class ExponentialBaseline(NoBaseline):
 
 
 class RolloutBaseline(NoBaseline):
-    """baselines.py:160-248 (greedy rollout of a frozen copy; the t-test epoch update is left to
-    the caller: `update(policy)` swaps the frozen copy)."""
+    """baselines.py:160-248: greedy rollout of a frozen copy of the policy; at the end of every epoch the current
+    policy challenges it on a fixed evaluation dataset and replaces it when it is better by a one-sided paired
+    t-test at level `bl_alpha` (`epoch_callback`)."""
 
-    def __init__(self):
+    def __init__(self, bl_alpha: float = 0.05, **kw):
+        self.bl_alpha = bl_alpha
         self.policy = None
+        self.dataset = None
+        self.bl_vals = None
+        self.mean = None
 
-    def setup(self, policy, *a, **k):
-        self.update(policy)
+    def setup(self, policy, env=None, batch_size=64, device=None, dataset_size=None, dataset=None, **kw):
+        self._update_policy(policy, env, batch_size, device, dataset_size, dataset)
 
     def update(self, policy):
+        """Swap the frozen copy without touching the evaluation dataset (kept from round 1)."""
         self.policy = copy.deepcopy(policy).eval()
         for p in self.policy.parameters():
             p.requires_grad_(False)
+
+    def _update_policy(self, policy, env=None, batch_size=64, device=None, dataset_size=None, dataset=None):
+        """baselines.py:174-189"""
+        self.update(policy)
+        if device is not None:
+            self.policy = self.policy.to(device)
+        if env is None:
+            return
+        if dataset is not None:
+            self.dataset = dataset
+        elif self.dataset is None and dataset_size:
+            self.dataset = env.dataset(batch_size=[dataset_size])
+        if self.dataset is not None:
+            dev = device if device is not None else next(self.policy.parameters()).device
+            self.bl_vals = self.rollout(self.policy, env, batch_size, dev, self.dataset).cpu().numpy()
+            self.mean = self.bl_vals.mean()
 
     def eval(self, td, reward, env=None):
         with torch.inference_mode():
             out = self.policy(td, env, phase="test", decode_type="greedy")
         return out["reward"].clone(), 0
 
+    def epoch_callback(self, policy, env, batch_size=64, device=None, epoch=None, dataset_size=None, **kw):
+        """baselines.py:200-217: replace the baseline policy if the candidate is significantly better."""
+        from scipy.stats import ttest_rel
+
+        dev = device if device is not None else next(policy.parameters()).device
+        candidate_vals = self.rollout(policy, env, batch_size, dev).cpu().numpy()
+        candidate_mean = candidate_vals.mean()
+        updated = False
+        if candidate_mean - self.mean > 0:
+            t, p = ttest_rel(-candidate_vals, -self.bl_vals)  # costs: inverse logic
+            p_val = p / 2  # one-sided
+            assert t < 0, "T-statistic should be negative"
+            if p_val < self.bl_alpha:
+                self._update_policy(policy, env, batch_size, dev, dataset_size)
+                updated = True
+        return updated
+
+    def rollout(self, policy, env, batch_size=64, device=None, dataset=None):
+        """baselines.py:219-237: greedy rewards of `policy` over a dataset, batch by batch."""
+        from torch.utils.data import DataLoader
+
+        dataset = self.dataset if dataset is None else dataset
+        was_training = policy.training
+        policy.eval()
+        rewards = []
+        with torch.inference_mode():
+            for batch in DataLoader(dataset, batch_size=batch_size, collate_fn=dataset.collate_fn):
+                td = env.reset(batch.to(device) if device is not None else batch)
+                rewards.append(policy(td, env, phase="test", decode_type="greedy")["reward"])
+        if was_training:
+            policy.train()
+        return torch.cat(rewards, 0)
+
+
+class WarmupBaseline(NoBaseline):
+    """baselines.py:91-134: convex combination of an exponential baseline and the wrapped baseline during the first
+    `n_epochs` epochs (alpha = (epoch + 1) / n_epochs after each epoch)."""
+
+    def __init__(self, baseline, n_epochs=1, warmup_exp_beta=0.8, **kw):
+        assert n_epochs > 0, "n_epochs to warmup must be positive"
+        self.baseline = baseline
+        self.warmup_baseline = ExponentialBaseline(warmup_exp_beta)
+        self.alpha = 0
+        self.n_epochs = n_epochs
+
+    def setup(self, *a, **k):
+        self.baseline.setup(*a, **k)
+
+    def eval(self, td, reward, env=None):
+        if self.alpha == 1:
+            return self.baseline.eval(td, reward, env)
+        if self.alpha == 0:
+            return self.warmup_baseline.eval(td, reward, env)
+        v_b, l_b = self.baseline.eval(td, reward, env)
+        v_wb, l_wb = self.warmup_baseline.eval(td, reward, env)
+        return self.alpha * v_b + (1 - self.alpha) * v_wb, self.alpha * l_b + (1 - self.alpha) * l_wb
+
+    def epoch_callback(self, *a, **kw):
+        self.baseline.epoch_callback(*a, **kw)
+        if kw["epoch"] < self.n_epochs:
+            self.alpha = (kw["epoch"] + 1) / float(self.n_epochs)
+
+
+class CriticNetwork(torch.nn.Module):
+    """models/rl/common/critic.py:11-63: encoder + value head (Linear E->512, ReLU, Linear 512->1), mean over nodes."""
+
+    def __init__(self, encoder, value_head=None, embed_dim: int = 128, hidden_dim: int = 512):
+        super().__init__()
+        self.encoder = encoder
+        if value_head is None:
+            value_head = torch.nn.Sequential(torch.nn.Linear(embed_dim, hidden_dim), torch.nn.ReLU(),
+                                             torch.nn.Linear(hidden_dim, 1))
+        self.value_head = value_head
+
+    def forward(self, x, hidden=None):
+        h, _ = self.encoder(x)
+        return self.value_head(h).mean(1)
+
+
+def create_critic_from_actor(policy, backbone: str = "encoder", **critic_kwargs):
+    """models/rl/common/critic.py:66-75"""
+    encoder = getattr(policy, backbone, None)
+    if encoder is None:
+        raise ValueError(f"CriticBaseline requires a backbone in the policy network: {backbone}")
+    return CriticNetwork(copy.deepcopy(encoder), **critic_kwargs).to(next(policy.parameters()).device)
+
+
+class CriticBaseline(NoBaseline):
+    """baselines.py:137-157: a critic network as baseline; its loss is mse(v, reward)."""
+
+    def __init__(self, critic=None, **unused_kw):
+        self.critic = critic
+
+    def setup(self, policy, env=None, **kwargs):
+        if self.critic is None:
+            self.critic = create_critic_from_actor(policy)
+
+    def eval(self, x, c, env=None):
+        v = self.critic(x).squeeze(-1)
+        return v.detach(), F.mse_loss(v, c.detach())
+
 
 def get_reinforce_baseline(name, **kw):
+    """baselines.py:251-287 (incl. the `warmup` wrapper: `with_warmup` / `n_epochs` / `exp_beta`)."""
     reg = {"no": NoBaseline, "shared": SharedBaseline, "mean": MeanBaseline, "exponential": ExponentialBaseline,
-           "rollout": RolloutBaseline}
+           "rollout_only": RolloutBaseline, "critic": CriticBaseline}
+    if name == "warmup":
+        inner = kw.get("baseline", "rollout")
+        if isinstance(inner, str):
+            inner = get_reinforce_baseline(inner, **{k: v for k, v in kw.items() if k != "baseline"})
+        return WarmupBaseline(inner, n_epochs=kw.get("n_epochs", 1), warmup_exp_beta=kw.get("warmup_exp_beta", 0.8))
+    if name == "rollout":  # the reference's "rollout" = one warm-up epoch of exponential baseline, then greedy rollout
+        return WarmupBaseline(RolloutBaseline(bl_alpha=kw.get("bl_alpha", 0.05)), kw.get("n_epochs", 1),
+                              kw.get("exp_beta", 0.8))
     if name not in reg:
-        raise ValueError(f"Unknown baseline {name}. Available baselines: {list(reg)}")
+        raise ValueError(f"Unknown baseline {name}. Available baselines: {list(reg) + ['rollout', 'warmup']}")
     return reg[name](**kw)
 
 

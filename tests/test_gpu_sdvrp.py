@@ -89,7 +89,10 @@ def test_sdvrp_decoder_step_vs_reference_logits(golden, name):
 
 @pytest.mark.parametrize("name", ["am_sdvrp20", "am_sdvrp50"])
 @pytest.mark.parametrize("mode", ["greedy", "sampling", "evaluate"])
-def test_sdvrp_policy_vs_golden(golden, name, mode, monkeypatch):
+@pytest.mark.parametrize("fused", [True, False])
+def test_sdvrp_policy_vs_golden(golden, name, mode, fused, monkeypatch):
+    """Both execution paths against the reference fixtures: the persistent kernel (ENV = sdvrp behind the mask
+    functor, dynamic embedding folded into per-step scalars) and the stepping kernels."""
     from rl4co_b200 import decoding
     from rl4co_b200.envs import get_env
     from rl4co_b200.tensordict import TensorDict
@@ -102,7 +105,13 @@ def test_sdvrp_policy_vs_golden(golden, name, mode, monkeypatch):
     td = env.reset(TensorDict(inst, batch_size=[B]))
     pol.encoder = _FixedEncoder(g["h"].to(DEV))
     kw = {}
-    if mode == "sampling":  # recorded-noise protocol: serve the Exp(1) draws torch.multinomial consumed, one per step
+    N = inst["locs"].shape[1] + 1
+    if mode == "sampling" and fused:  # recorded-noise protocol, padded to the kernel's step bound
+        q = g["sampling_noise"]
+        qpad = torch.ones(3 * (N - 1) + 2, q.shape[1], q.shape[2])
+        qpad[: q.shape[0]] = q
+        kw = dict(decode_type="sampling", noise=qpad.to(DEV))
+    elif mode == "sampling":  # stepping path: serve the Exp(1) draws torch.multinomial consumed, one per step
         served = iter(g["sampling_noise"].to(DEV).unbind(0))
         monkeypatch.setattr(decoding.Sampling, "_noise", lambda self, logits: next(served).contiguous())
         kw = dict(decode_type="sampling")
@@ -111,7 +120,7 @@ def test_sdvrp_policy_vs_golden(golden, name, mode, monkeypatch):
     else:
         kw = dict(decode_type="greedy")
     with torch.inference_mode():
-        out = pol(td, env, phase="test", return_sum_log_likelihood=False, **kw)
+        out = pol(td, env, phase="test", return_sum_log_likelihood=False, fused_rollout=fused, **kw)
     key = {"greedy": "greedy", "sampling": "sampling", "evaluate": "eval"}[mode]
     ra, rl, rr = g[f"{key}_actions"], g[f"{key}_logprobs"], g[f"{key}_reward"]
     if mode == "evaluate":
@@ -126,8 +135,9 @@ def test_sdvrp_policy_vs_golden(golden, name, mode, monkeypatch):
     torch.testing.assert_close(out["reward"].cpu()[same], rr[same], rtol=RTOL, atol=1e-6)
 
 
-@pytest.mark.parametrize("n,batch", [(20, 64), (50, 64), (100, 32)])
-def test_sdvrp_policy_vs_prefix_oracle(n, batch):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("n,batch", [(20, 64), (50, 64), (100, 32), (5, 40)])
+def test_sdvrp_policy_vs_prefix_oracle(n, batch, fused):
     """Seeded larger cases: every GPU choice is the oracle's (near-)best for the same prefix, log-probs / reward
     agree, tours are valid."""
     from rl4co_b200.envs import get_env
@@ -143,7 +153,8 @@ def test_sdvrp_policy_vs_prefix_oracle(n, batch):
     with torch.inference_mode():
         td = env.reset(td_host.to(DEV))
         h, _ = pol.encoder(td)
-        out = pol(td, env, phase="test", decode_type="greedy", return_sum_log_likelihood=False, encoder_output=(h, h))
+        out = pol(td, env, phase="test", decode_type="greedy", return_sum_log_likelihood=False, encoder_output=(h, h),
+                  fused_rollout=fused)
     W = {k: v.detach().cpu() for k, v in pol.state_dict().items()}
     inst = {k: td_host[k] for k in ("locs", "depot", "demand")}
     acts = out["actions"].cpu()
@@ -189,3 +200,29 @@ def test_sdvrp_under_the_reference_loop():
     assert same is not None and same.float().mean() >= 0.9
     torch.testing.assert_close(b["log_likelihood"][same], a["log_likelihood"][same], rtol=RTOL, atol=ATOL_LP)
     torch.testing.assert_close(b["reward"][same], a["reward"][same], rtol=RTOL, atol=1e-6)
+
+
+def test_sdvrp_fused_equals_stepping_and_multisample():
+    """Persistent kernel == stepping kernels on the same instances (greedy); in-kernel Philox sampling gives valid
+    split-delivery tours and reproducible draws."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(9)
+    env = get_env("sdvrp", generator_params=dict(num_loc=50), check_solution=True)
+    pol = FusedAttentionModelPolicy(env_name="sdvrp", num_encoder_layers=1).to(DEV).eval()
+    pol.decoder.cache_gemm = "cublas"
+    with torch.inference_mode():
+        td = env.reset(env.generator(256).to(DEV))
+        a = pol(td, env, phase="test", decode_type="greedy", return_sum_log_likelihood=False)
+        b = pol(td, env, phase="test", decode_type="greedy", return_sum_log_likelihood=False, fused_rollout=False)
+        T = min(a["actions"].shape[1], b["actions"].shape[1])
+        same = (a["actions"][:, :T] == b["actions"][:, :T]).all(1)
+        assert same.float().mean() >= 0.95
+        torch.testing.assert_close(a["reward"][same], b["reward"][same], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(a["log_likelihood"][:, :T][same], b["log_likelihood"][:, :T][same], rtol=RTOL, atol=ATOL_LP)
+        s1 = pol(td, env, phase="train", decode_type="sampling", seed=4)   # check_solution=True validates the tours
+        s2 = pol(td, env, phase="train", decode_type="sampling", seed=4)
+        s3 = pol(td, env, phase="train", decode_type="sampling", seed=5)
+    assert torch.equal(s1["actions"], s2["actions"]) and not torch.equal(s1["actions"], s3["actions"])
+    assert torch.isfinite(s1["log_likelihood"]).all() and (s1["log_likelihood"] < 0).all()

@@ -330,3 +330,36 @@ def test_bench_reference_arm_line_schema():
 
     assert line["cpu_baseline"]["kind"] == ("reference" if ref_standin.reference_available() else "port")
     assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["single_process"]["value"] > 0
+
+
+def test_seeded_dataset_generation_matches_reference(tmp_path):
+    """data/generate_data.py:37-76,213-317: the numpy-seeded validation / test sets are bit-identical to the
+    reference's; `env.dataset(phase=...)` loads them."""
+    import importlib
+
+    import numpy as np
+
+    from oracle import ref_standin
+    from rl4co_b200 import data as D
+    from rl4co_b200.envs import get_env
+
+    files = D.generate_default_datasets(str(tmp_path), dataset_size=16, graph_sizes=(20, 50))
+    assert len(files) == 8 and all(os.path.isfile(f) for f in files)
+    assert os.path.basename(files[0]) == "tsp20_val_seed4321.npz" and os.path.basename(files[-1]) == "vrp50_test_seed1234.npz"
+    if ref_standin.reference_available():
+        ref_standin.install()
+        G = importlib.import_module("rl4co.data.generate_data")
+        for prob, gs, seed, name in (("tsp", 20, 4321, "val"), ("vrp", 50, 1234, "test")):
+            np.random.seed(seed)
+            want = G.generate_env_data(prob, 16, gs, None)
+            got = np.load(D.dataset_filename(str(tmp_path), prob, gs, name, seed))
+            assert set(got.files) == set(want.keys())
+            for k in want:
+                assert np.array_equal(got[k], want[k]), (prob, k)
+    env = get_env("cvrp", generator_params=dict(num_loc=20), data_dir=str(tmp_path), val_file="vrp/vrp20_val_seed4321.npz")
+    ds = env.dataset(phase="val")
+    assert len(ds) == 16
+    raw = np.load(D.dataset_filename(str(tmp_path), "vrp", 20, "val", 4321))
+    np.testing.assert_allclose(ds[0]["demand"].numpy(), raw["demand"][0] / raw["capacity"][0])  # cvrp/env.py:179-186
+    assert len(env.dataset(batch_size=[5], phase="train")) == 5          # no train file: generated
+    assert len(env.dataset(batch_size=[7], phase="test")) == 7           # test file unset: generated
