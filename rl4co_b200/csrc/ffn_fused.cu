@@ -36,7 +36,7 @@ constexpr int TILE_B = 128 * 32 * 4;                         // one [128 x 32] o
 constexpr int OFF_W = 2 * KB * TILE_B;                       // after x hi / lo
 constexpr int WST = 3;                                       // weight ring stages (hi + lo each): 2 blocks in flight
 constexpr int SMEM_B = OFF_W + WST * 2 * TILE_B;             // 229 376 (x 128 KB + 3 x 32 KB)
-constexpr int THREADS = 320;                                 // warps 0-3 x producers, 4-7 epilogue, 8 issuer, 9 weight loader
+constexpr int THREADS = 448;   // warps 0-3 x producers, 4-7 + 10-13 epilogue (two column halves), 8 issuer, 9 weight loader
 constexpr int CLUSTER = 2;                                   // CTAs sharing every weight block
 constexpr int WBLOCK_FLOATS = 2 * 128 * 32;                  // one pre-tiled block: hi image, lo image (32 KB)
 constexpr uint32_t SBO = 1024, COL_HLO = 256, COL_Y = 384;
@@ -186,7 +186,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
   }
   if (tid == 0) {
     auto init = [&](uint32_t bar, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); };
-    init(XFULL(), 128); init(XEMPTY(), 1); init(HPFULL(), 128); init(HFREE(), 1); init(YFULL(), 1); init(YEMPTY(), 128);
+    init(XFULL(), 128); init(XEMPTY(), 1); init(HPFULL(), 256); init(HFREE(), 1); init(YFULL(), 1); init(YEMPTY(), 256);
     for (int s = 0; s < WST; ++s) { init(WFULL(s), 1); init(WEMPTY(s), CLUSTER); }
     for (int s = 0; s < 2; ++s) init(HFULL(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -305,7 +305,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps 4..7: one row per thread
-    const int q4 = warp & 3, row_in_tile = 32 * q4 + lane;  // (warps 4..7: TMEM lane quarter = warp % 4)
+    // two groups of four warps (4..7 and 10..13), each covering the four TMEM lane quarters (quarter = warp % 4) and
+    // one half of the columns: the per-chunk epilogue has to finish inside one FF1 (3 072 cycles of MMAs)
+    const int q4 = warp & 3, row_in_tile = 32 * q4 + lane, eg = (warp >= 10) ? 1 : 0;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q4) << 16);
     uint32_t c = 0;
     uint32_t r[32];
@@ -339,21 +341,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
             tmem_st16(lane_base + COL_HLO + cc * 32 + 16 * half, lo);
           }
         };
+        // this warp group's half of the chunk: columns [64 * eg, 64 * eg + 64)
         uint32_t r2[32];
-        tmem_ld32_issue(hcol, r);
+        tmem_ld32_issue(hcol + 64 * eg, r);
         tmem_ld_wait(r);
         // H_lo is single-buffered: FF2 of the previous chunk must have retired before it is overwritten
         if (c >= 1) bar_wait(HFREE(), (c - 1) & 1);
-        tmem_ld32_issue(hcol + 32, r2);
-        process(r, 0);
+        tmem_ld32_issue(hcol + 64 * eg + 32, r2);
+        process(r, 2 * eg);
         tmem_ld_wait(r2);
-        tmem_ld32_issue(hcol + 64, r);
-        process(r2, 1);
-        tmem_ld_wait(r);
-        tmem_ld32_issue(hcol + 96, r2);
-        process(r, 2);
-        tmem_ld_wait(r2);
-        process(r2, 3);
+        process(r2, 2 * eg + 1);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_before();
         bar_arrive(HPFULL());
@@ -361,7 +358,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
       // final epilogue: Y + b2 + x, BN, store (a lane writes complete 128-byte lines of its own row)
       bar_wait(YFULL(), t & 1);
       tc_after();
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 2 * eg; cc < 2 * eg + 2; ++cc) {
         tmem_ld32(lane_base + COL_Y + cc * 32, r);
         if (row < g.M) {
           const float4* xr = reinterpret_cast<const float4*>(g.x + (size_t)row * g.ldx + cc * 32);
