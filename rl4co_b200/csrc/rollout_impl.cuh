@@ -72,9 +72,9 @@ struct Smem {
   float ll_acc;
   // sdvrp (dynamic embedding, nn/env_embeddings/dynamic.py:60-78): the remaining demand d_n adds d_n * w to node n's
   // glimpse key / value / folded logit key; everything the step needs beyond d_n is a per-node or per-step scalar
-  float wdyn[3 * E];                // [wk | wv | W_out^T wl]
-  float pwk[32 * SPL * 8 + 8];      // ptab[n] . wk_h per (node, head); last 8 = the zero row
-  float ol[8];                      // per-head o_h . wl'_h of the current step
+  alignas(16) float wdyn[3 * E];    // [wk | wv | W_out^T wl]
+  alignas(16) float pwk[32 * SPL * 8 + 8];  // ptab[n] . wk_h per (node, head); last 8 = the zero row
+  alignas(16) float ol[8];          // per-head o_h . wl'_h of the current step (read as two float4)
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
