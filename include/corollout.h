@@ -265,6 +265,35 @@ int co_dihedral8(const float* locs, float* out, long B, int N, void* stream);
  * 8 heads x 16, no mask, fp32 -> out [B*N, E] ("h d"); N <= 128. */
 int co_encoder_mha(const float* qkv, float* out, int B, int N, void* stream);
 
+/* ------------------------------------------------------------------ training step: differentiable attention core
+ * (SURVEY.md 8f-2).  o = softmax(q k^T / sqrt(16) [masked]) v per head, 8 heads x 16 channels, fp32; forward saves the
+ * per-row log-sum-exp (log2 units of the scaled scores), backward recomputes the probabilities -- no [M, N] tensor in
+ * memory.  Replaces F.scaled_dot_product_attention under autograd in the AM encoder
+ * (rl4co/models/nn/attention.py:110-134) and in the glimpse of the teacher-forced log-likelihood pass
+ * (nn/attention.py:300-314 with the T decode steps of an instance as T queries; utils/decoding.py:448-461).
+ * All tensors are [B, rows, 128] with the head slice h at column 16 h, last dimension contiguous; row / batch strides
+ * (in floats, multiples of 4) are free, so column views of the fused cache or of a packed qkv projection need no
+ * copy.  mask: [B, M, 4] uint32, bit n % 32 of word n / 32 set = key n may be attended (NULL = no mask); a fully
+ * masked row yields o = 0.  N <= 128 keys, M <= 256 queries per call. */
+typedef struct co_attn_args {
+  const float* q;        /* [B, M, E] */
+  const float* k;        /* [B, N, E] */
+  const float* v;        /* [B, N, E] */
+  const uint32_t* mask;  /* [B, M, 4] or NULL */
+  float* o;              /* [B, M, E]   (forward: out; backward: in) */
+  float* lse;            /* [B, 8, M]   (forward: out; backward: in) */
+  const float* dO;       /* [B, M, E], strides of o; backward only */
+  float* dq;             /* [B, M, E] backward out */
+  float* dk;             /* [B, N, E] backward out */
+  float* dv;             /* [B, N, E] backward out */
+  int32_t B, M, N, reserved0;
+  int64_t q_bs, k_bs, v_bs, o_bs, dq_bs, dk_bs, dv_bs; /* batch strides (floats) */
+  int32_t q_rs, k_rs, v_rs, o_rs, dq_rs, dk_rs, dv_rs; /* row strides (floats)   */
+  float scale;                                         /* 1 / sqrt(head_dim) = 0.25 */
+} co_attn_args;
+int co_attn_fwd(const co_attn_args* args, void* stream);
+int co_attn_bwd(const co_attn_args* args, void* stream);
+
 /* REINFORCE baseline statistics (rl4co/models/rl/reinforce/baselines.py:75-81):
  * out[0] += sum(reward), out[1] += count, in float64 so the cross-rank sum is
  * order-independent enough to reproduce the single-process mean. */

@@ -1,5 +1,5 @@
 // Persistent whole-episode rollout kernel (the north-star kernel) -- implementation header,
-// instantiated per environment in rollout_tsp.cu / rollout_cvrp.cu.
+// instantiated per environment in rollout_tsp.cu / rollout_cvrp.cu / rollout_sdvrp.cu.
 //
 // Replaces the `while not td["done"].all()` loop of ConstructivePolicy.forward
 // (rl4co/models/common/constructive/base.py:219-251): per node selection it fuses
@@ -10,29 +10,30 @@
 //   TSPEnv._step / CVRPEnv._step       envs/routing/tsp/env.py:60-86, cvrp/env.py:66-136
 // and at the end get_reward (ops.py:82-90) and get_log_likelihood (decoding.py:38-62).
 //
-// Design (B200): one CTA (256 threads = 8 warps) owns one instance for its whole episode.
-//   * warp h holds head h of glimpse_key / glimpse_val for all nodes IN REGISTERS as float2
-//     pairs (lane l owns nodes l, l+32, ..) and uses Blackwell's packed FFMA2; the glimpse
-//     (scores -> masked softmax -> weighted value sum) is warp-local: one REDUX.MAX on an
-//     order-preserving integer key, one shuffle all-reduce, one shared-memory transpose;
-//   * logit_key is pre-multiplied by project_out on the host side of the cache
-//     (logits = heads . (L W_out)[n]) and also lives in registers: thread (node, part) owns
-//     16*SPL contiguous channels of its node;
-//   * the per-node context table (node_emb @ Wctx_cur^T) sits in shared memory, so the next
-//     query is one row read + the per-episode fixed part;
-//   * the log-softmax uses the tanh-clip bound as its fixed offset (z <= clip/T), so per-warp
-//     partial sums add up without any exp in the cross-warp combine; arg-max is REDUX.MAX +
-//     ballot; sampling is arg-max of z - log q (Gumbel form of torch.multinomial's p/q);
-//   * each thread keeps only the visited bits it needs (its glimpse slots + its logits node);
-//     capacity / current node are replicated scalars; the CVRP depot rule uses a register bitmask
-//     over demand ranks (ffs = unvisited customer of least demand) instead of a block-wide OR;
+// Design (B200, fourth version -- the per-phase cycle budget it was derived from is in
+// profiles/r02_rollout_phase_budget.txt): one CTA (256 threads = 8 warps) owns one instance for its whole episode.
+//   * warp h holds head h of glimpse_key, glimpse_val AND of the folded logit key (logit_key @ project_out, so that
+//     logits = sum_h o_h . L'_h[n]) for all nodes IN REGISTERS as float2 pairs (lane l owns nodes SPL*l .. SPL*l+SPL-1)
+//     and uses Blackwell's packed FFMA2.  Glimpse AND the head's share of every pointer logit are warp-local: one
+//     REDUX.MAX on an order-preserving integer key, one shared-memory transpose for the value reduction, a 16-float
+//     broadcast of the un-normalised head output, and the 1/sum(exp) normalisation applied to the SPL partial logits
+//     (its shuffle reduction hides under the FFMA2s).  The version before read all 128 head outputs back per thread
+//     (16 LDS.128 per warp-step, LSU-bound: 318 of 2 160 cycles per selection); now a warp reads 4.
+//   * barrier 1; thread n < NS sums the eight per-head partials of node n, tanh-clip, mask, temperature; the warp's
+//     arg-max is REDUX.MAX + ballot (lowest node wins ties, torch semantics); sampling = arg-max of z - log q
+//     (Gumbel form of torch.multinomial's p/q); barrier 2; every thread merges the <= 4 per-warp winners.
+//   * the log-probability of the chosen node is NOT on the critical path: z of the last two steps stays in shared
+//     memory and a warp that has no logits work computes log-softmax(z)[a] of the PREVIOUS step while the others are
+//     in the tanh / arg-max phase (exact exp-sum with the tanh-clip bound as fixed offset, z <= clip/T).
+//   * the per-node context table (node_emb @ Wctx_cur^T) sits in shared memory, so the next query is one row read +
+//     the per-episode fixed part; each thread keeps only the visited bits it needs; capacity / current node are
+//     replicated scalars; the CVRP depot rule uses a register bitmask over demand ranks instead of a block-wide OR;
 //   * exactly two block barriers per node selection; no state in HBM.
 // HBM traffic per instance = one read of its cache rows + T*(8+4) B of outputs.
 //
-// Cache layouts (args.cache_width): 4E = [K | V | L' | cur-table] (default): the TSP first-node half of the context
-// projection is NOT a per-node table (only one row per episode was ever read) but one 128x128 GEMV per episode from
-// node_emb / w_first;  5E (tsp) = [K | V | L' | first-table | cur-table], still accepted (the multistart kernel reads
-// one table row per start).
+// Cache layouts (args.cache_width): 4E = [K | V | L' | cur-table]: the TSP first-node half of the context
+// projection is one 128x128 GEMV per episode from node_emb / w_first;  5E (tsp default) = [K | V | L' | first-table |
+// cur-table] (the multistart kernel reads one table row per start).
 #pragma once
 #include "co_common.cuh"
 
@@ -44,11 +45,8 @@ namespace co {
 
 template <int SPL>
 struct Cfg {
-  static constexpr int NS = 32 * SPL;       // node slots
-  static constexpr int PARTS = 8 / SPL;     // threads sharing one node in the logits phase
-  static constexpr int NPW = 32 / PARTS;    // nodes per warp in the logits phase
-  static constexpr int EPP = 16 * SPL;      // channels of logit_key per thread
-  static constexpr int OPAD = EPP + 4;      // padded stride of a part's chunk in `o` (bank spread)
+  static constexpr int NS = 32 * SPL;  // node slots
+  static constexpr int NW = SPL;       // warps of the selection phase: thread n < NS owns node n there
   static constexpr int MINB = SPL == 4 ? 1 : (SPL == 2 ? 2 : 3);
 };
 
@@ -56,25 +54,24 @@ constexpr int TILE_LD = 20;  // padded row of the per-warp AV transpose tile
 
 template <int SPL>
 struct Smem {
-  float ptab[(32 * SPL + 1) * E];   // current-node context table; last row = zeros
-  float qfix[E];                    // per-episode fixed part of the query
-  float wcap[E];                    // cvrp: remaining-capacity column of project_context
-  float hfirst[E];                  // tsp, 4E cache: embedding of the first node (GEMV operand; 16-byte aligned)
-  float o[8 * (16 * SPL + 4) + 8];  // concatenated heads (padded per part)
-  float tile[8][32 * TILE_LD];      // per-warp transpose tile for the value reduction
-  unsigned red_key[8];              // per-warp best key (order-preserving uint of a float)
-  int red_idx[8];                   // per-warp arg-max node
-  float red_sum[8];                 // per-warp sum exp(z - Zb)
+  float ptab[(32 * SPL + 1) * E];       // current-node context table; last row = zeros
+  float qfix[E];                        // per-episode fixed part of the query
+  float wcap[E];                        // cvrp: remaining-capacity column of project_context
+  float hfirst[E];                      // tsp, 4E cache: embedding of the first node (GEMV operand; 16-byte aligned)
+  float tile[8][32 * TILE_LD];          // per-warp transpose tile for the value reduction
+  alignas(16) float oh[8][D];           // per-warp broadcast of the un-normalised head output
+  alignas(16) float part[8][32 * SPL];  // per-head share of every pointer logit: [head][node]
+  alignas(16) float zbuf[2][32 * SPL];  // masked, temperature-scaled logits of the last two steps (deferred log-prob)
+  alignas(16) uint2 red[4];             // per selection warp: (best key as order-preserving uint, node)
+  alignas(16) float lps[32];            // log-prob warp: lane partial sums of exp(z - Zb)
   float dem[32 * SPL];
   float2 loc[32 * SPL];
-  unsigned char order[32 * SPL];    // cvrp: customers sorted by demand (ascending)
-  unsigned char rank_of[32 * SPL];  // cvrp: demand rank of each customer (inverse of `order`)
-  float ll_acc;
+  unsigned char order[32 * SPL];        // cvrp: customers sorted by demand (ascending)
+  unsigned char rank_of[32 * SPL];      // cvrp: demand rank of each customer (inverse of `order`)
   // sdvrp (dynamic embedding, nn/env_embeddings/dynamic.py:60-78): the remaining demand d_n adds d_n * w to node n's
   // glimpse key / value / folded logit key; everything the step needs beyond d_n is a per-node or per-step scalar
-  alignas(16) float wdyn[3 * E];    // [wk | wv | W_out^T wl]
-  alignas(16) float pwk[32 * SPL * 8 + 8];  // ptab[n] . wk_h per (node, head); last 8 = the zero row
-  alignas(16) float ol[8];          // per-head o_h . wl'_h of the current step (read as two float4)
+  alignas(16) float wdyn[3 * E];              // [wk | wv | W_out^T wl]
+  alignas(16) float pwk[32 * SPL * 8 + 8];    // ptab[n] . wk_h per (node, head); last 8 = the zero row
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -95,6 +92,19 @@ __device__ __forceinline__ unsigned fkey(float f) {
 }
 __device__ __forceinline__ float funkey(unsigned k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// Warp sum of non-negative lane values whose total is <= 128 (softmax numerators after the max subtraction, <= 4 per
+// lane), through two REDUX.SUM on a 48-bit fixed-point split instead of a five-deep shuffle chain: x * 2^24 is split
+// exactly into an integer part and a fraction (fmaf of an exactly representable difference); the result is the fp32
+// rounding of a sum that is exact to 2^-48 per lane -- order independent, and at least as accurate as an fp32 tree.
+__device__ __forceinline__ float warp_sum_fixed(float x) {
+  constexpr float S = 16777216.f;
+  const unsigned hi = __float2uint_rz(x * S);
+  const float rem = fmaf(x, S, -(float)hi);
+  const unsigned lo = __float2uint_rz(rem * S);
+  const unsigned Hs = __reduce_add_sync(FULL, hi), Ls = __reduce_add_sync(FULL, lo);
+  return fmaf((float)Ls, 1.0f / (S * S), (float)Hs * (1.0f / S));
 }
 
 // tsp, 4E cache: qfix[e] += sum_c w_first[e][c] * hfirst[c]  (project_context[:, :E] @ h[first], context.py:129-133).
@@ -128,7 +138,7 @@ __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used
 template <int SPL, int ENV, int MODE, int CWB>  // CWB = cache blocks of E floats per node row: 4, or 5 (tsp first-node table)
 __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_rollout_args A) {
   using C = Cfg<SPL>;
-  constexpr int NS = C::NS, PARTS = C::PARTS, NPW = C::NPW, EPP = C::EPP, OPAD = C::OPAD;
+  constexpr int NS = C::NS, NW = C::NW;
   constexpr int CW = CWB * E;        // cache row width: 4E, or 5E (tsp with the first-node table)
   constexpr int CUR_BLK = CWB - 1;   // block holding the current-node table (always the last one)
   constexpr bool first_table = (ENV == CO_ENV_TSP) && (CWB == 5);
@@ -143,45 +153,40 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
   const int B_traj = B_inst * S;
   const bool forced_start = (S > 1) && (A.flags & CO_ROLLOUT_FORCED_START);
   const bool philox = (A.noise == nullptr);
-  const int nL = h * NPW + lane / PARTS;  // node owned in the logits phase
-  const int part = lane % PARTS;
+  const bool sel_warp = h < NW;   // selection phase: thread tid < NS owns node nL = tid
+  const bool lp_warp = h == NW;   // the warp that computes the previous step's log-probability meanwhile
+  const int nL = sel_warp ? tid : NS - 1;
+  const int nG = SPL * lane;      // first of this lane's SPL consecutive glimpse nodes
   const float clip = A.tanh_clipping, inv_temp = 1.0f / A.temperature;
   const float Zb = clip * inv_temp;       // z = clip*tanh(.)/T <= Zb: fixed log-softmax offset
   float* tile = sm.tile[h];
 
-  float2 Kr[SPL][8], Vr[SPL][8], Lr[EPP / 2];
+  float2 Kr[SPL][8], Vr[SPL][8], Lr[SPL][8];
 
   for (int b = blockIdx.x; b < B_inst; b += gridDim.x) {
     __syncthreads();  // previous instance no longer reads shared memory
     const float* crow = A.cache + (size_t)b * N * CW;
-    // ---- one HBM read of the instance: registers <- glimpse_key/val head slices, folded logit key
+    // ---- one HBM read of the instance: registers <- head slices of glimpse_key / glimpse_val / folded logit key
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
-      const int n = lane + 32 * k;
+      const int n = nG + k;
       if (n < N) {
         const float4* ks = reinterpret_cast<const float4*>(crow + (size_t)n * CW + 0 * E + h * D);
         const float4* vs = reinterpret_cast<const float4*>(crow + (size_t)n * CW + 1 * E + h * D);
+        const float4* ls = reinterpret_cast<const float4*>(crow + (size_t)n * CW + 2 * E + h * D);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 kv = __ldg(ks + c), vv = __ldg(vs + c);
+          const float4 kv = __ldg(ks + c), vv = __ldg(vs + c), lv = __ldg(ls + c);
           Kr[k][2 * c] = make_float2(kv.x, kv.y); Kr[k][2 * c + 1] = make_float2(kv.z, kv.w);
           Vr[k][2 * c] = make_float2(vv.x, vv.y); Vr[k][2 * c + 1] = make_float2(vv.z, vv.w);
+          Lr[k][2 * c] = make_float2(lv.x, lv.y); Lr[k][2 * c + 1] = make_float2(lv.z, lv.w);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { Kr[k][j] = make_float2(0.f, 0.f); Vr[k][j] = make_float2(0.f, 0.f); }
+        for (int j = 0; j < 8; ++j) {
+          Kr[k][j] = make_float2(0.f, 0.f); Vr[k][j] = make_float2(0.f, 0.f); Lr[k][j] = make_float2(0.f, 0.f);
+        }
       }
-    }
-    if (nL < N) {
-      const float4* ls = reinterpret_cast<const float4*>(crow + (size_t)nL * CW + 2 * E + part * EPP);
-#pragma unroll
-      for (int c = 0; c < EPP / 4; ++c) {
-        const float4 lv = __ldg(ls + c);
-        Lr[2 * c] = make_float2(lv.x, lv.y); Lr[2 * c + 1] = make_float2(lv.z, lv.w);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < EPP / 2; ++c) Lr[c] = make_float2(0.f, 0.f);
     }
     // ---- shared memory <- context table, coordinates, demands
     for (int idx = tid; idx < N * (E / 4); idx += 256) {
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     }
     float dmk0[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; ++k) dmk0[k] = sm.dem[lane + 32 * k];
+    for (int k = 0; k < SPL; ++k) dmk0[k] = sm.dem[nG + k];
     const float dL0 = sm.dem[nL];
     // scores split by linearity: q.K = ptab[cur].K + qfix.K + rem * (wcap.K); the last two are
     // per-episode / per-instance constants held in registers (FK, WK)
@@ -267,12 +272,11 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     for (int k = 0; k < SPL; ++k) { WK[k] = 0.f; FK[k] = 0.f; }
     if (VRP) head_dot(sm.wcap, WK);
     // sdvrp per-instance / per-lane constants of the dynamic terms
-    float WKW = 0.f, wv_d = 0.f, wl_d = 0.f;
+    float WKW = 0.f, wv_d = 0.f;
     if (SD) {
 #pragma unroll
       for (int c = 0; c < D; ++c) WKW = fmaf(sm.wcap[h * D + c], sm.wdyn[h * D + c], WKW);  // wcap_h . wk_h
       wv_d = sm.wdyn[E + h * D + (lane & 15)];
-      wl_d = sm.wdyn[2 * E + h * D + (lane & 15)];
     }
     if (!(A.flags & CO_ROLLOUT_NO_PREFETCH) && b + (int)gridDim.x < B_inst) {  // next instance's cache rows -> L2
       const char* nxt = reinterpret_cast<const char*>(A.cache + (size_t)(b + gridDim.x) * N * CW);
@@ -285,11 +289,11 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       int64_t* act_row = A.actions_out + (size_t)traj * T_max;
       float* lp_row = A.logp_out + (size_t)traj * T_max;
       // ---------------- reset (tsp/env.py:88-113, cvrp/env.py:98-124)
-      // visited flags this thread needs: bit k = its glimpse slot lane+32k, bit 8 = its logits node nL
+      // visited flags this thread needs: bit k = its glimpse node nG + k, bit 8 = its selection-phase node nL
       // (padding slots start as visited)
-      uint32_t mybits = (nL >= N) ? 0x100u : 0u;
+      uint32_t mybits = (!sel_warp || nL >= N) ? 0x100u : 0u;
 #pragma unroll
-      for (int k = 0; k < SPL; ++k) mybits |= (lane + 32 * k >= N) ? (1u << k) : 0u;
+      for (int k = 0; k < SPL; ++k) mybits |= (nG + k >= N) ? (1u << k) : 0u;
       int cur = (ENV == CO_ENV_TSP) ? NS : 0;  // NS -> zero row: step-0 placeholder context
       int prev = 0, first = 0, t = 0, dstep = 0, nvis = 0;
       // cvrp: visited customers as a bitmask over demand RANKS (bits >= #customers pre-set), so the
@@ -302,26 +306,26 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       float used = 0.f, dist = 0.f;
       bool anyfeas = false, done = false, depot_seen = false;
-      // (remaining) demand of this thread's glimpse nodes / logits node: constant for cvrp, dynamic for sdvrp
+      // (remaining) demand of this thread's glimpse nodes / selection node: constant for cvrp, dynamic for sdvrp
       float dmk[SPL], dL = dL0;
 #pragma unroll
       for (int k = 0; k < SPL; ++k) dmk[k] = dmk0[k];
       int nrem = 0;                 // sdvrp: customers with demand left
       int pend_a = -1;              // sdvrp: demand write-back deferred past the next barrier (see env_step)
       float pend_d = 0.f, FKW = 0.f;
-      __syncthreads();  // previous trajectory finished with qfix / ll_acc
+      float ll = 0.f;               // log-likelihood, accumulated by lane 0 of the log-prob warp
+      __syncthreads();  // previous trajectory finished with qfix
       if (tid < E) {
         float g = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;
         if (ENV == CO_ENV_TSP && !forced_start) g += A.q_placeholder[tid];
         sm.qfix[tid] = g;
       }
-      if (tid == 0) sm.ll_acc = 0.f;
 
       // one environment transition, replicated in every thread
       auto env_step = [&](int a) {
         if (!SD) {  // (sdvrp: nodes may be revisited; mybits only flags the padding slots there)
-#pragma unroll
-          for (int k = 0; k < SPL; ++k) mybits |= (a == lane + 32 * k) ? (1u << k) : 0u;
+          const unsigned dd = (unsigned)(a - nG);
+          mybits |= (dd < (unsigned)SPL) ? (1u << dd) : 0u;
           mybits |= (a == nL) ? 0x100u : 0u;
         }
         if (h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           used = (used + delivered) * (a != 0 ? 1.0f : 0.0f);
           const float d_new = d_a + (-delivered);  // scatter_add(-1, a, -delivered)
 #pragma unroll
-          for (int k = 0; k < SPL; ++k) dmk[k] = (a == lane + 32 * k) ? d_new : dmk[k];
+          for (int k = 0; k < SPL; ++k) dmk[k] = (a == nG + k) ? d_new : dmk[k];
           dL = (a == nL) ? d_new : dL;
           nrem += ((d_new > 0.f) ? 1 : 0) - ((d_a > 0.f) ? 1 : 0);
           pend_a = a; pend_d = d_new;
@@ -368,6 +372,31 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         prev = a; cur = a; ++t;
         // cvrp: all nodes incl. the depot visited; sdvrp: no positive demand left (sdvrp/env.py:71)
         done = (ENV == CO_ENV_TSP) ? (t >= N) : (SD ? (nrem == 0) : (nvis >= N));
+      };
+      // log-softmax(z)[a] of one finished step from its z row (log-prob warp; decoding.py:188,352-356): exact
+      // exp-sum with the fixed offset Zb; masked nodes hold -inf -> 2^-inf = 0
+      auto logp_of = [&](int buf, int a_sel, int t_out) {
+        const float* zb = sm.zbuf[buf];
+        float sacc = 0.f;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) sacc += ex2((zb[nG + k] - Zb) * LOG2E);
+        // 32 lane partials -> every lane adds all of them in a fixed tree from shared memory (shorter dependent
+        // chain than five shuffles; this warp must finish inside the other warps' selection phase)
+        sm.lps[lane] = sacc;
+        __syncwarp();
+        const float4* lq = reinterpret_cast<const float4*>(sm.lps);
+        const float4 q0 = lq[0], q1 = lq[1], q2 = lq[2], q3 = lq[3], q4 = lq[4], q5 = lq[5], q6 = lq[6], q7 = lq[7];
+        const float t0 = ((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w));
+        const float t1 = ((q2.x + q2.y) + (q2.z + q2.w)) + ((q3.x + q3.y) + (q3.z + q3.w));
+        const float t2 = ((q4.x + q4.y) + (q4.z + q4.w)) + ((q5.x + q5.y) + (q5.z + q5.w));
+        const float t3 = ((q6.x + q6.y) + (q6.z + q6.w)) + ((q7.x + q7.y) + (q7.z + q7.w));
+        sacc = (t0 + t1) + (t2 + t3);
+        __syncwarp();  // lps is rewritten by the next call
+        const float lp = (zb[a_sel] - Zb) - lg2(sacc) * LN2;
+        if (lane == 0) {
+          lp_row[t_out] = lp;
+          ll += lp;
+        }
       };
 
       if (SD) {  // customers with demand: counted by every thread from shared memory (uniform)
@@ -398,13 +427,13 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         int forced = 0;
         float gum = 0.f;  // -log q, q ~ Exp(1): Gumbel perturbation for sampling
         if (MODE == CO_MODE_EVALUATE) forced = (int)A.forced_actions[(size_t)traj * T_max + t];
-        if (MODE == CO_MODE_SAMPLE && part == 0 && nL < N) {
-          const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstep, nL)
-                                 : A.noise[((size_t)dstep * B_traj + traj) * N + nL];
+        if (MODE == CO_MODE_SAMPLE && tid < N) {
+          const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstep, tid)
+                                 : A.noise[((size_t)dstep * B_traj + traj) * N + tid];
           gum = -logf(q);
         }
 
-        // ---------------- glimpse: warp h = head h, fully warp-local
+        // ---------------- glimpse + this head's share of every pointer logit: warp h = head h, fully warp-local
         {
           const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur * E + h * D);
           const float rem = cap - used;  // context.py:147-149
@@ -427,7 +456,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           const float qwk = SD ? fmaf(rem, WKW, sm.pwk[cur * 8 + h] + FKW) : 0.f;
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
-            fz[k] = feasible<ENV>(lane + 32 * k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
+            fz[k] = feasible<ENV>(nG + k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
             float dot = (sc2[k].x + sc2[k].y) + FK[k];
             if (VRP) dot = fmaf(rem, WK[k], dot);
             if (SD) dot = fmaf(dmk[k], qwk, dot);  // q . (K[n] + d_n wk) = q.K[n] + d_n (q.wk)
@@ -452,7 +481,6 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           float4* trow = reinterpret_cast<float4*>(tile + lane * TILE_LD);
 #pragma unroll
           for (int c = 0; c < 4; ++c) trow[c] = make_float4(acc[2 * c].x, acc[2 * c].y, acc[2 * c + 1].x, acc[2 * c + 1].y);
-          esum = warp_sum(esum);
           if (SD) sed = warp_sum(sed);
           __syncwarp();
           const int d = lane & 15, half = lane >> 4;
@@ -467,83 +495,78 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           float r = (s0 + s1) + (s2 + s3);
           r += __shfl_xor_sync(FULL, r, 16);
           if (SD) r = fmaf(sed, wv_d, r);  // + (sum_n e_n d_n) * wv_h[d]
-          const float ov = __fdividef(r, esum);
-          if (lane < 16) {
-            const int e = h * D + d;
-            sm.o[e + 4 * (e / EPP)] = ov;
+          if (lane < 16) sm.oh[h][lane] = r;  // un-normalised head output (d == lane here)
+          __syncwarp();
+          // share of head h in the pointer logits of this lane's nodes: (o_h / esum) . L'_h[n]  (+ sdvrp: d_n (o_h . wl'_h))
+          const float4* op = reinterpret_cast<const float4*>(sm.oh[h]);
+          float2 pl2[SPL];
+          float olh = 0.f;
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) pl2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 x = op[c];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) {
+              pl2[k] = ffma2(make_float2(x.x, x.y), Lr[k][2 * c], pl2[k]);
+              pl2[k] = ffma2(make_float2(x.z, x.w), Lr[k][2 * c + 1], pl2[k]);
+            }
+            if (SD) {
+              const float4 w = reinterpret_cast<const float4*>(sm.wdyn + 2 * E + h * D)[c];
+              olh = fmaf(x.x, w.x, olh); olh = fmaf(x.y, w.y, olh); olh = fmaf(x.z, w.z, olh); olh = fmaf(x.w, w.w, olh);
+            }
           }
-          if (SD) {  // o_h . wl'_h for the dynamic logit term (16 lanes hold the head's 16 channels)
-            float t4 = ov * wl_d;
-            t4 += __shfl_xor_sync(FULL, t4, 8);
-            t4 += __shfl_xor_sync(FULL, t4, 4);
-            t4 += __shfl_xor_sync(FULL, t4, 2);
-            t4 += __shfl_xor_sync(FULL, t4, 1);
-            if (lane == 0) sm.ol[h] = t4;
+          esum = warp_sum_fixed(esum);  // 0 <= e <= 1 per node: two REDUX.SUM, independent of the FFMA2 block above
+          const float rinv = __fdividef(1.0f, esum);
+          float pl[SPL];
+#pragma unroll
+          for (int k = 0; k < SPL; ++k) {
+            float v = pl2[k].x + pl2[k].y;
+            if (SD) v = fmaf(dmk[k], olh, v);
+            pl[k] = v * rinv;
           }
+          float* pdst = sm.part[h] + nG;
+          if (SPL == 4) *reinterpret_cast<float4*>(pdst) = make_float4(pl[0], pl[SPL > 1 ? 1 : 0], pl[SPL > 2 ? 2 : 0], pl[SPL > 3 ? 3 : 0]);
+          else if (SPL == 2) *reinterpret_cast<float2*>(pdst) = make_float2(pl[0], pl[SPL > 1 ? 1 : 0]);
+          else *pdst = pl[0];
         }
-        __syncthreads();  // B1: heads complete
+        __syncthreads();  // B1: every head's share of every logit is in shared memory
 
-        // ---------------- pointer logits + tanh clip + mask: thread (nL, part)
         if (SD && tid == 0 && pend_a >= 0) sm.dem[pend_a] = pend_d;  // deferred demand write-back (every thread is
                                                                      // past the env_step that read the old value)
-        const bool fzL = feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
-        float z;
-        {
-          const float4* ov = reinterpret_cast<const float4*>(sm.o + part * OPAD);
-          float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
-#pragma unroll
-          for (int c = 0; c < EPP / 4; c += 2) {
-            const float4 x = ov[c], y = ov[c + 1];
-            p0 = ffma2(make_float2(x.x, x.y), Lr[2 * c], p0);
-            p1 = ffma2(make_float2(x.z, x.w), Lr[2 * c + 1], p1);
-            p2 = ffma2(make_float2(y.x, y.y), Lr[2 * c + 2], p2);
-            p3 = ffma2(make_float2(y.z, y.w), Lr[2 * c + 3], p3);
-          }
-          float p = ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
-#pragma unroll
-          for (int off = PARTS / 2; off > 0; off >>= 1) p += __shfl_xor_sync(FULL, p, off);
-          if (SD) {  // + d_n * (o . wl'): the dynamic logit-key term, heads summed in fixed order
-            const float4 u0 = reinterpret_cast<const float4*>(sm.ol)[0], u1 = reinterpret_cast<const float4*>(sm.ol)[1];
-            p = fmaf(dL, ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w)), p);
-          }
+        if (sel_warp) {
+          // ---------------- pointer logit of node nL: heads summed in fixed order, tanh clip, mask, temperature
+          const bool fzL = feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
+          const float p = ((sm.part[0][nL] + sm.part[1][nL]) + (sm.part[2][nL] + sm.part[3][nL])) +
+                          ((sm.part[4][nL] + sm.part[5][nL]) + (sm.part[6][nL] + sm.part[7][nL]));
           const float lg = tanhf(p * 0.08838834764831845f) * clip;  // /sqrt(E), tanh clip (decoding.py:169-170)
-          z = fzL ? lg * inv_temp : -INFINITY;                       // mask, temperature (decoding.py:173-177)
-        }
-        {
-          const float ex = (part == 0) ? ex2((z - Zb) * LOG2E) : 0.f;  // exp(z - Zb) in (0,1]; 0 if masked
-          const float wsum = warp_sum(ex);
-          const float keyf = (MODE == CO_MODE_SAMPLE) ? ((part == 0 && fzL) ? z + gum : -INFINITY) : z;
-          const unsigned key = fkey(keyf);
-          const unsigned wkey = __reduce_max_sync(FULL, key);
-          const unsigned vote = __ballot_sync(FULL, key == wkey);
-          if (lane == 0) {
-            sm.red_key[h] = wkey;
-            sm.red_idx[h] = h * NPW + (__ffs(vote) - 1) / PARTS;  // first lane wins ties = lowest node
-            sm.red_sum[h] = wsum;
+          const float z = fzL ? lg * inv_temp : -INFINITY;          // mask, temperature (decoding.py:173-177)
+          sm.zbuf[dstep & 1][nL] = z;
+          if (MODE != CO_MODE_EVALUATE) {
+            const float keyf = (MODE == CO_MODE_SAMPLE) ? (fzL ? z + gum : -INFINITY) : z;
+            const unsigned key = fkey(keyf);
+            const unsigned wkey = __reduce_max_sync(FULL, key);
+            const unsigned vote = __ballot_sync(FULL, key == wkey);
+            if (lane == 0) sm.red[h] = make_uint2(wkey, (unsigned)(32 * h + __ffs(vote) - 1));  // lowest node wins ties
           }
+        } else if (lp_warp && dstep > 0) {
+          logp_of((dstep - 1) & 1, prev, t - 1);  // the previous step's log-probability, off the critical path
         }
-        __syncthreads();  // B2: per-warp partials complete
+        __syncthreads();  // B2: per-warp winners complete
         int a;
-        float Ssum;
-        {
-          const uint4 k0 = reinterpret_cast<const uint4*>(sm.red_key)[0], k1 = reinterpret_cast<const uint4*>(sm.red_key)[1];
-          const int4 i0 = reinterpret_cast<const int4*>(sm.red_idx)[0], i1 = reinterpret_cast<const int4*>(sm.red_idx)[1];
-          const float4 u0 = reinterpret_cast<const float4*>(sm.red_sum)[0], u1 = reinterpret_cast<const float4*>(sm.red_sum)[1];
-          Ssum = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
-          unsigned bk = k0.x; a = i0.x;  // strict '>' keeps the lowest warp (= lowest node) on ties
-          if (k0.y > bk) { bk = k0.y; a = i0.y; }
-          if (k0.z > bk) { bk = k0.z; a = i0.z; }
-          if (k0.w > bk) { bk = k0.w; a = i0.w; }
-          if (k1.x > bk) { bk = k1.x; a = i1.x; }
-          if (k1.y > bk) { bk = k1.y; a = i1.y; }
-          if (k1.z > bk) { bk = k1.z; a = i1.z; }
-          if (k1.w > bk) { bk = k1.w; a = i1.w; }
-        }
-        if (MODE == CO_MODE_EVALUATE) a = (forced < 0 || forced >= N) ? 0 : forced;
-        if (nL == a && part == 0) {  // log_softmax of the chosen node: (z - Zb) - log(sum exp(z - Zb))
-          const float lpL = (z - Zb) - lg2(Ssum) * LN2;
-          lp_row[t] = lpL;
-          sm.ll_acc += lpL;
+        if (MODE == CO_MODE_EVALUATE) {
+          a = (forced < 0 || forced >= N) ? 0 : forced;
+        } else if (NW == 1) {
+          a = (int)sm.red[0].y;
+        } else if (NW == 2) {
+          const uint4 r0 = reinterpret_cast<const uint4*>(sm.red)[0];
+          a = (int)((r0.z > r0.x) ? r0.w : r0.y);  // strict '>' keeps the lower warp (= lowest node) on ties
+        } else {
+          const uint4 r0 = reinterpret_cast<const uint4*>(sm.red)[0], r1 = reinterpret_cast<const uint4*>(sm.red)[1];
+          const bool b01 = r0.z > r0.x, b23 = r1.z > r1.x;
+          const unsigned ka = b01 ? r0.z : r0.x, ia = b01 ? r0.w : r0.y;
+          const unsigned kb = b23 ? r1.z : r1.x, ib = b23 ? r1.w : r1.y;
+          a = (int)((kb > ka) ? ib : ia);
         }
         if (tid == 0) act_row[t] = a;
 
@@ -560,13 +583,16 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         }
       }
 
-      // ---------------- epilogue: reward, log-likelihood, padding
+      // ---------------- epilogue: last log-probability, reward, log-likelihood, padding
       __syncthreads();
+      if (lp_warp) {
+        if (dstep > 0) logp_of((dstep - 1) & 1, prev, t - 1);
+        if (lane == 0) A.loglik_out[traj] = ll;
+      }
       if (tid == 0) {
         const float2 pa = sm.loc[(ENV == CO_ENV_TSP) ? first : 0], pp = sm.loc[prev];
         const float dx = pa.x - pp.x, dy = pa.y - pp.y;
         A.reward_out[traj] = -(dist + sqrtf(dx * dx + dy * dy));
-        A.loglik_out[traj] = sm.ll_acc;
         if (A.steps_out) A.steps_out[traj] = t;
         if (A.used_capacity_out) A.used_capacity_out[traj] = used;
         if (A.max_steps_out) atomicMax(A.max_steps_out, t);

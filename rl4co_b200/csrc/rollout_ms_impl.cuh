@@ -22,6 +22,15 @@ namespace co {
 constexpr int MSQ = 4;  // trajectories per pass
 
 template <int SPL>
+struct CfgMS {  // logits phase of this kernel: thread (node, part) owns 16*SPL contiguous channels of its node
+  static constexpr int NS = 32 * SPL;       // node slots
+  static constexpr int PARTS = 8 / SPL;     // threads sharing one node in the logits phase
+  static constexpr int NPW = 32 / PARTS;    // nodes per warp in the logits phase
+  static constexpr int EPP = 16 * SPL;      // channels of logit_key per thread
+  static constexpr int OPAD = EPP + 4;      // padded stride of a part's chunk in `o` (bank spread)
+};
+
+template <int SPL>
 struct SmemMS {
   float ptab[(32 * SPL + 1) * E];          // current-node context table; last row = zeros
   float lkey[32 * SPL * (E + 4 * (8 / SPL))];  // folded logit key, row = PARTS chunks of (EPP + 4)
@@ -41,7 +50,7 @@ struct SmemMS {
 
 template <int SPL, int ENV, int MODE>
 __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_args A) {
-  using C = Cfg<SPL>;
+  using C = CfgMS<SPL>;
   constexpr int NS = C::NS, PARTS = C::PARTS, NPW = C::NPW, EPP = C::EPP, OPAD = C::OPAD;
   constexpr int LROW = E + 4 * PARTS;                    // padded logit-key row (floats)
   constexpr int CW = (ENV == CO_ENV_TSP ? 5 : 4) * E;

@@ -45,6 +45,13 @@ class VRPInitEmbedding(nn.Module):
         return torch.cat((depot_embedding, node_embeddings), -2)
 
 
+def _train_attention_on(x, n_keys: int, num_heads: int) -> bool:
+    import os
+
+    return (x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and x.shape[-1] == 128 and num_heads == 8
+            and n_keys <= 128 and os.environ.get("CO_TRAIN_ATTN", "fused") != "sdpa")
+
+
 class SkipConnection(nn.Module):
     def __init__(self, module):
         super().__init__()
@@ -63,7 +70,14 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, x):
         B, N, _ = x.shape
-        q, k, v = self.Wqkv(x).view(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
+        qkv = self.Wqkv(x)
+        if _train_attention_on(x, N, self.num_heads):
+            # autograd path of the training step: hand-written forward / backward (co_attn_fwd / co_attn_bwd) on the
+            # packed projection instead of torch's fp32 mem-efficient SDPA; CO_TRAIN_ATTN=sdpa forces the stock op
+            from . import attention_train
+
+            return self.out_proj(attention_train.self_attention_packed(qkv))
+        q, k, v = qkv.view(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4).unbind(0)
         out = F.scaled_dot_product_attention(q, k, v)
         return self.out_proj(out.transpose(1, 2).reshape(B, N, -1))
 

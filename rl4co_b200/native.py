@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
 SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
-           "ffn_fused.cu", "data_kernels.cu"]
+           "ffn_fused.cu", "data_kernels.cu", "attn_train.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
@@ -40,7 +40,7 @@ EXPORTS = [
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
     "co_ffn_fused", "co_ffn_tile_weights", "co_ffn_tiled_weight_floats", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
-    "co_sdvrp_step", "co_sdvrp_action_mask",
+    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd",
 ]
 
 
@@ -66,6 +66,14 @@ class RolloutArgs(Structure):
         ("node_emb", c_void_p), ("w_first", c_void_p), ("cache_width", c_int32), ("reserved0", c_int32),
         ("dyn_w", c_void_p),
     ]
+
+
+class AttnArgs(Structure):
+    _fields_ = ([(n, c_void_p) for n in ("q", "k", "v", "mask", "o", "lse", "dO", "dq", "dk", "dv")]
+                + [(n, c_int32) for n in ("B", "M", "N", "reserved0")]
+                + [(n, ctypes.c_int64) for n in ("q_bs", "k_bs", "v_bs", "o_bs", "dq_bs", "dk_bs", "dv_bs")]
+                + [(n, c_int32) for n in ("q_rs", "k_rs", "v_rs", "o_rs", "dq_rs", "dk_rs", "dv_rs")]
+                + [("scale", c_float)])
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -135,6 +143,8 @@ def lib() -> ctypes.CDLL:
     L.co_sdvrp_step.argtypes = [c_void_p] * 9 + [c_int, c_int, c_void_p]
     L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.co_attn_fwd.argtypes = [POINTER(AttnArgs), c_void_p]
+    L.co_attn_bwd.argtypes = [POINTER(AttnArgs), c_void_p]
     L.co_cache_width.argtypes = [c_int]
     L.co_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_void_p]
     L.co_gemm_tf32x3.argtypes = [c_void_p] * 8 + [c_int] * 7 + [c_void_p]
@@ -414,6 +424,59 @@ def dihedral8(locs):
     out = torch.empty(8 * B, N, 2, dtype=F32, device=locs.device)
     _check(lib().co_dihedral8(_ptr(locs, F32, "locs"), _ptr(out, F32, "out"), B, N, _stream()), "co_dihedral8")
     return out
+
+
+def _attn_view(t, name, rows=None):
+    """[B, rows, 128] fp32 CUDA tensor whose last dimension is contiguous -> (ptr, batch stride, row stride)."""
+    if t.dim() != 3 or t.shape[-1] != EMBED_DIM or t.stride(-1) != 1:
+        raise ValueError(f"{name}: expected [B, rows, {EMBED_DIM}] with a contiguous last dimension, got {tuple(t.shape)} / {t.stride()}")
+    if rows is not None and t.shape[1] != rows:
+        raise ValueError(f"{name}: expected {rows} rows, got {t.shape[1]}")
+    bs, rs = (t.stride(0) if t.shape[0] > 1 else t.shape[1] * t.stride(1)), t.stride(1)
+    if bs % 4 or rs % 4 or t.data_ptr() % 16:
+        raise ValueError(f"{name}: strides must be multiples of 4 floats and the base 16-byte aligned")
+    return _ptr(t, F32, name, strided=True), bs, rs
+
+
+def _attn_args(q, k, v, mask_words, o, lse):
+    B, M, _ = q.shape
+    N = k.shape[1]
+    a = AttnArgs()
+    a.q, a.q_bs, a.q_rs = _attn_view(q, "q")
+    a.k, a.k_bs, a.k_rs = _attn_view(k, "k")
+    a.v, a.v_bs, a.v_rs = _attn_view(v, "v", N)
+    a.o, a.o_bs, a.o_rs = _attn_view(o, "o", M)
+    if mask_words is not None:
+        if tuple(mask_words.shape) != (B, M, 4) or mask_words.dtype != torch.int32:
+            raise ValueError(f"mask_words: expected int32 [{B}, {M}, 4], got {mask_words.dtype} {tuple(mask_words.shape)}")
+        a.mask = _ptr(mask_words, torch.int32, "mask_words")
+    if tuple(lse.shape) != (B, NUM_HEADS, M):
+        raise ValueError(f"lse: expected [{B}, {NUM_HEADS}, {M}], got {tuple(lse.shape)}")
+    a.lse = _ptr(lse, F32, "lse")
+    a.B, a.M, a.N = B, M, N
+    a.scale = 0.25
+    return a
+
+
+@_on_device_of_first_tensor
+def attn_fwd(q, k, v, mask_words, o, lse):
+    """co_attn_fwd: o, lse <- attention(q, k, v[, mask]); q [B,M,E], k / v [B,N,E] (strided views allowed)."""
+    a = _attn_args(q, k, v, mask_words, o, lse)
+    _check(lib().co_attn_fwd(ctypes.byref(a), _stream()), "co_attn_fwd")
+    return o
+
+
+@_on_device_of_first_tensor
+def attn_bwd(q, k, v, mask_words, o, lse, dO, dq, dk, dv):
+    """co_attn_bwd: dq, dk, dv <- gradients of attention(q, k, v[, mask]) given dO (same strides as o)."""
+    a = _attn_args(q, k, v, mask_words, o, lse)
+    if dO.shape != o.shape or dO.stride() != o.stride():
+        raise ValueError("dO must have the shape and strides of o")
+    a.dO = _ptr(dO, F32, "dO", strided=True)
+    a.dq, a.dq_bs, a.dq_rs = _attn_view(dq, "dq", q.shape[1])
+    a.dk, a.dk_bs, a.dk_rs = _attn_view(dk, "dk", k.shape[1])
+    a.dv, a.dv_bs, a.dv_rs = _attn_view(dv, "dv", k.shape[1])
+    _check(lib().co_attn_bwd(ctypes.byref(a), _stream()), "co_attn_bwd")
 
 
 @_on_device_of_first_tensor

@@ -110,8 +110,17 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     def heads(x):
         return x.view(x.shape[0], x.shape[1], H, -1).transpose(1, 2)
 
-    o = F.scaled_dot_product_attention(heads(q), heads(K), heads(V), attn_mask=mask[:, None])
-    o = o.transpose(1, 2).reshape(B, Q, E)
+    import os
+
+    if q.is_cuda and N <= 128 and q.dtype == torch.float32 and os.environ.get("CO_TRAIN_ATTN", "fused") != "sdpa":
+        # the T (x S) decode steps of an instance are independent queries against its cached K / V: hand-written
+        # masked attention forward / backward (co_attn_fwd / co_attn_bwd) on the cache's column views, no copies
+        from . import attention_train
+
+        o = attention_train.attention(q.contiguous(), K, V, mask)
+    else:
+        o = F.scaled_dot_product_attention(heads(q), heads(K), heads(V), attn_mask=mask[:, None])
+        o = o.transpose(1, 2).reshape(B, Q, E)
     glimpse = dec.pointer.project_out(o)
     logits = torch.bmm(glimpse, L.transpose(1, 2)) / math.sqrt(E)
     clip = policy.tanh_clipping if tanh_clipping is None else tanh_clipping
