@@ -294,6 +294,13 @@ typedef struct co_attn_args {
 int co_attn_fwd(const co_attn_args* args, void* stream);
 int co_attn_bwd(const co_attn_args* args, void* stream);
 
+/* Instance normalisation of the encoder (nn.InstanceNorm1d(E, affine=True) on x.permute(0,2,1),
+ * rl4co/models/nn/ops.py:30-54; POMO's `normalization="instance"`): per (instance, channel) mean / biased variance over
+ * the N nodes, y = (x - mean) / sqrt(var + eps) * gamma + beta.  x, out [B, N, 128] contiguous (out may alias x);
+ * gamma / beta [128] or NULL. */
+int co_instance_norm(const float* x, const float* gamma, const float* beta, float* out, long B, int N, float eps,
+                     void* stream);
+
 /* REINFORCE baseline statistics (rl4co/models/rl/reinforce/baselines.py:75-81):
  * out[0] += sum(reward), out[1] += count, in float64 so the cross-rank sum is
  * order-independent enough to reproduce the single-process mean. */

@@ -230,6 +230,17 @@ class AttentionModelEncoder(nn.Module):
                 and tuple(lins[1].weight.shape) == (128, 512) and type(ffn) is MLP)  # MLP: ReLU between the two Linear
 
     @staticmethod
+    def _apply_norm(norm, h, B, N, E):
+        """Non-batch normalisation of the fused path: instance norm on co_instance_norm, anything else stock."""
+        from . import native
+
+        m = norm.normalizer
+        if (isinstance(m, nn.InstanceNorm1d) and not m.track_running_stats and h.is_cuda and E == native.EMBED_DIM
+                and h.dtype == torch.float32):
+            return native.instance_norm(h.view(B, N, E), m.weight, m.bias, m.eps).view(B * N, E)
+        return norm(h.view(B, N, E)).reshape(B * N, E).contiguous()
+
+    @staticmethod
     def _bn_affine(norm):
         bn = norm.normalizer
         if not isinstance(bn, nn.BatchNorm1d):
@@ -259,7 +270,7 @@ class AttentionModelEncoder(nn.Module):
                                        scale=aff[0], shift=aff[1])
             else:
                 h = native.gemm_tf32x3(att, *self._split(mha.out_proj.weight), bias=mha.out_proj.bias, residual=h)
-                h = norm1(h.view(B, N, E)).reshape(B * N, E).contiguous()
+                h = self._apply_norm(norm1, h, B, N, E)
             lins = ffn.lins
             aff = self._bn_affine(norm2)
             if self._ffn_fusable(ffn):
@@ -268,7 +279,7 @@ class AttentionModelEncoder(nn.Module):
                 h = native.ffn_fused(h, self._ffn_tiled(lins[0].weight, lins[1].weight), lins[0].bias, lins[1].bias,
                                      scale=aff[0] if aff is not None else None, shift=aff[1] if aff is not None else None)
                 if aff is None:
-                    h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()
+                    h = self._apply_norm(norm2, h, B, N, E)
                 continue
             f = h
             for lin in lins[:-1]:
@@ -281,5 +292,5 @@ class AttentionModelEncoder(nn.Module):
             else:
                 h = native.gemm_tf32x3(f, *self._split(last.weight), bias=last.bias, residual=h)
             if aff is None:
-                h = norm2(h.view(B, N, E)).reshape(B * N, E).contiguous()
+                h = self._apply_norm(norm2, h, B, N, E)
         return h.view(B, N, E)

@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
 SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
-           "ffn_fused.cu", "data_kernels.cu", "attn_train.cu"]
+           "ffn_fused.cu", "data_kernels.cu", "attn_train.cu", "norm_kernels.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
@@ -40,7 +40,7 @@ EXPORTS = [
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
     "co_ffn_fused", "co_ffn_tile_weights", "co_ffn_tiled_weight_floats", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
-    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd",
+    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd", "co_instance_norm",
 ]
 
 
@@ -143,6 +143,7 @@ def lib() -> ctypes.CDLL:
     L.co_sdvrp_step.argtypes = [c_void_p] * 9 + [c_int, c_int, c_void_p]
     L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.co_instance_norm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_float, c_void_p]
     L.co_attn_fwd.argtypes = [POINTER(AttnArgs), c_void_p]
     L.co_attn_bwd.argtypes = [POINTER(AttnArgs), c_void_p]
     L.co_cache_width.argtypes = [c_int]
@@ -423,6 +424,18 @@ def dihedral8(locs):
     B, N, _ = locs.shape
     out = torch.empty(8 * B, N, 2, dtype=F32, device=locs.device)
     _check(lib().co_dihedral8(_ptr(locs, F32, "locs"), _ptr(out, F32, "out"), B, N, _stream()), "co_dihedral8")
+    return out
+
+
+@_on_device_of_first_tensor
+def instance_norm(x, gamma=None, beta=None, eps: float = 1e-5, out=None):
+    """co_instance_norm: nn.InstanceNorm1d(E, affine) over the node dimension of x [B, N, 128] (contiguous)."""
+    if x.dim() != 3 or x.shape[-1] != EMBED_DIM:
+        raise ValueError(f"x: expected [B, N, {EMBED_DIM}], got {tuple(x.shape)}")
+    if out is None:
+        out = torch.empty_like(x)
+    _check(lib().co_instance_norm(_ptr(x, F32, "x"), _ptr(gamma, F32, "gamma"), _ptr(beta, F32, "beta"),
+                                  _ptr(out, F32, "out"), x.shape[0], x.shape[1], float(eps), _stream()), "co_instance_norm")
     return out
 
 

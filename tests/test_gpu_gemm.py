@@ -112,3 +112,24 @@ def test_encoder_fused_ffn_equals_split_path(monkeypatch):
         monkeypatch.delenv("CO_FFN")
         h_fused, _ = pol.encoder(td)
     torch.testing.assert_close(h_fused, h_split, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(7, 100), (3, 20), (5, 128), (2, 2), (700, 51)])
+def test_instance_norm_matches_torch(B, N):
+    """co_instance_norm == nn.InstanceNorm1d(E, affine=True) on x.permute(0, 2, 1) (rl4co/models/nn/ops.py:30-54)."""
+    from rl4co_b200 import native
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(B * 31 + N)
+    x = torch.randn(B, N, 128, device=dev) * 3.0 + 0.7
+    m = torch.nn.InstanceNorm1d(128, affine=True).to(dev)
+    with torch.no_grad():
+        m.weight.uniform_(0.5, 1.5)
+        m.bias.uniform_(-0.5, 0.5)
+        ref = m(x.permute(0, 2, 1)).permute(0, 2, 1)
+        ref64 = torch.nn.functional.instance_norm(x.double().permute(0, 2, 1), weight=m.weight.double(), bias=m.bias.double(),
+                                                  eps=m.eps).permute(0, 2, 1)
+        out = native.instance_norm(x, m.weight, m.bias, m.eps)
+    torch.testing.assert_close(out.double(), ref64, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=2e-6)
