@@ -65,14 +65,14 @@ __device__ __forceinline__ void store_row(float* p, const Row& r, float mul) {
 }
 // dot of a register row with a shared-memory row (warp-uniform address: broadcast)
 __device__ __forceinline__ float dot_s(const Row& a, const float4* s) {
-  float2 acc = make_float2(0.f, 0.f);
+  float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;  // two chains of four: half the dependent latency
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 x = s[i];
-    acc = ffma2(a.c[2 * i], make_float2(x.x, x.y), acc);
-    acc = ffma2(a.c[2 * i + 1], make_float2(x.z, x.w), acc);
+    acc0 = ffma2(a.c[2 * i], make_float2(x.x, x.y), acc0);
+    acc1 = ffma2(a.c[2 * i + 1], make_float2(x.z, x.w), acc1);
   }
-  return acc.x + acc.y;
+  return (acc0.x + acc1.x) + (acc0.y + acc1.y);
 }
 __device__ __forceinline__ void axpy_s(Row& y, float a, const float4* s) {  // y += a * s
   const float2 a2 = make_float2(a, a);
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const co_attn_args A) {
   const float4* K4 = reinterpret_cast<const float4*>(Ks);
   const float4* V4 = reinterpret_cast<const float4*>(Vs);
   float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 2
   for (int j = 0; j < N; ++j) {
     const float s0 = dot_s(q0, K4 + 4 * j), s1 = dot_s(q1, K4 + 4 * j);
     m0 = bit(w0, j) ? fmaxf(m0, s0) : m0;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const co_attn_args A) {
   }
   Row a0 = zero_row(), a1 = zero_row();
   float l0 = 0.f, l1 = 0.f;
+#pragma unroll 2
   for (int j = 0; j < N; ++j) {
     const float s0 = dot_s(q0, K4 + 4 * j), s1 = dot_s(q1, K4 + 4 * j);
     const float p0 = bit(w0, j) ? ex2(s0 - m0) : 0.f;
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const co_attn_args A) 
   const float4* K4 = reinterpret_cast<const float4*>(Ks);
   const float4* V4 = reinterpret_cast<const float4*>(Vs);
   Row dq0 = zero_row(), dq1 = zero_row();
+#pragma unroll 2
   for (int j = 0; j < N; ++j) {
     const float s0 = dot_s(q0, K4 + 4 * j), s1 = dot_s(q1, K4 + 4 * j);
     const float dp0 = dot_s(g0, V4 + 4 * j), dp1 = dot_s(g1, V4 + 4 * j);
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(64) attn_bwd_dkv_kernel(const co_attn_args A) 
   const float4* G4 = reinterpret_cast<const float4*>(Gs);
   const int wsel0 = j0 >> 5, wsel1 = j1 >> 5;
   const uint32_t bit0 = 1u << (j0 & 31), bit1 = has1 ? (1u << (j1 & 31)) : 0u;
+#pragma unroll 2
   for (int i = 0; i < M; ++i) {
     const float s0 = dot_s(k0, Q4 + 4 * i), s1 = dot_s(k1, Q4 + 4 * i);
     const float dp0 = dot_s(v0, G4 + 4 * i), dp1 = dot_s(v1, G4 + 4 * i);

@@ -189,11 +189,15 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
     }
     // ---- shared memory <- context table, coordinates, demands
+    // (cp.async: the ~13 16-byte copies of a thread are all in flight at once; the LDG -> STS loop this replaces
+    // waited for every load before the next one was issued and was a fifth of the per-instance prologue)
     for (int idx = tid; idx < N * (E / 4); idx += 256) {
       const int n = idx >> 5, c = idx & 31;
-      reinterpret_cast<float4*>(sm.ptab + n * E)[c] =
-          __ldg(reinterpret_cast<const float4*>(crow + (size_t)n * CW + CUR_BLK * E) + c);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(sm.ptab + n * E) + c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                   "l"(reinterpret_cast<const float4*>(crow + (size_t)n * CW + CUR_BLK * E) + c) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     if (tid < E) {
       sm.ptab[NS * E + tid] = 0.f;
       sm.wcap[tid] = VRP ? A.w_capacity[tid] : 0.f;
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     const float cap = (VRP && A.vehicle_capacity) ? A.vehicle_capacity[b] : 1.0f;
     // cvrp: fp32 add, as `td["vehicle_capacity"] + 1e-5`; sdvrp compares `used >= vehicle_capacity` (no slack)
     const float thr = SD ? cap : cap + 1e-5f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (SD) {  // per-(node, head) dot of the context-table row with the dynamic key weight
       for (int i = tid; i < (NS + 1) * 8; i += 256) {

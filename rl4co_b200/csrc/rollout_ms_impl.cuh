@@ -2,15 +2,20 @@
 // trajectories of an instance share its K / V / logit-key (am/decoder.py:178-179 shares them the
 // same way through `unbatchify`), so this variant advances Q = 4 trajectories per pass.
 //
-// Same structure and numerics as rollout_impl.cuh (read that header first); differences:
+// Same numerics as rollout_impl.cuh (read that header first); structure:
 //   * every phase handles the Q trajectories of the group before the block barrier, written
 //     stage-major in straight-line code so that their independent instruction streams interleave
 //     (a warp issues in order: a per-trajectory loop would serialise the chains and gain nothing --
 //     measured); the two barriers and the serial REDUX / MUFU / shuffle / LDS latencies are thereby
-//     amortised over Q node selections (the single-trajectory kernel is latency-bound at 37 % issue use);
-//   * the folded logit key lives in shared memory (padded rows, conflict-free LDS.128) instead of
-//     registers -- it is read once per pass and reused by the Q queries -- which frees the
-//     registers for the per-trajectory state and accumulators;
+//     amortised over Q node selections;
+//   * glimpse_key / glimpse_val head slices live in registers (warp h = head h, lane l owns nodes l + 32 k);
+//     the folded logit key lives in shared memory HEAD-MAJOR ([head][16-byte chunk][node], conflict-free
+//     LDS.128): after its glimpse warp h reads its 16 un-normalised head outputs of the Q trajectories back
+//     (16 broadcast LDS.128) and its own slice of the logit key ONCE per pass (4 x SPL LDS.128), and adds head
+//     h's share of every pointer logit of the Q trajectories (the version before read all 128 head outputs per
+//     thread and trajectory: 64 broadcast LDS.128 per thread and pass, the LSU-bound part of the pass);
+//   * selection: thread (node, group): the 256 threads split into 256 / NS groups that take Q * NS / 256
+//     trajectories each, sum the eight per-head shares, tanh / mask / temperature, per-warp arg-max and exp-sum;
 //   * trajectories that are done (CVRP: variable length) are still computed but their results are
 //     discarded by predication; the group ends when all of its trajectories are done.
 // Layout of results is unchanged: row j = s * B + b (start-major, rl4co/utils/ops.py:10-29).
@@ -22,25 +27,25 @@ namespace co {
 constexpr int MSQ = 4;  // trajectories per pass
 
 template <int SPL>
-struct CfgMS {  // logits phase of this kernel: thread (node, part) owns 16*SPL contiguous channels of its node
-  static constexpr int NS = 32 * SPL;       // node slots
-  static constexpr int PARTS = 8 / SPL;     // threads sharing one node in the logits phase
-  static constexpr int NPW = 32 / PARTS;    // nodes per warp in the logits phase
-  static constexpr int EPP = 16 * SPL;      // channels of logit_key per thread
-  static constexpr int OPAD = EPP + 4;      // padded stride of a part's chunk in `o` (bank spread)
+struct CfgMS {
+  static constexpr int NS = 32 * SPL;                    // node slots
+  static constexpr int G = 256 / NS;                     // selection groups of NS threads (2 / 4 / 8)
+  static constexpr int TPG = (MSQ >= G) ? MSQ / G : 1;   // trajectories per selection group (2 / 1 / 1)
+  static constexpr int GA = MSQ / TPG;                   // groups that have selection work (2 / 4 / 4)
 };
 
 template <int SPL>
 struct SmemMS {
   float ptab[(32 * SPL + 1) * E];          // current-node context table; last row = zeros
-  float lkey[32 * SPL * (E + 4 * (8 / SPL))];  // folded logit key, row = PARTS chunks of (EPP + 4)
+  float4 lkh[8 * 4 * 32 * SPL];            // folded logit key, head-major: [head][chunk of 4 channels][node]
   float qfix[MSQ][E];                      // per-trajectory fixed part of the query
   float wcap[E];
-  float o[MSQ][8 * (16 * SPL + 4) + 8];    // concatenated heads per trajectory (padded per part)
+  alignas(16) float oh[8][MSQ][D];         // per-warp un-normalised head outputs of the Q trajectories
   float tile[8][2][32 * TILE_LD];          // per-warp ping-pong transpose tiles
-  unsigned red_key[MSQ][8];
-  int red_idx[MSQ][8];
-  float red_sum[MSQ][8];
+  float part[MSQ][8][32 * SPL];            // per-head share of every pointer logit: [trajectory][head][node]
+  alignas(16) unsigned red_key[MSQ][4];    // per selection warp of the trajectory's group
+  alignas(16) int red_idx[MSQ][4];
+  alignas(16) float red_sum[MSQ][4];
   float dem[32 * SPL];
   float2 loc[32 * SPL];
   unsigned char order[32 * SPL];
@@ -51,8 +56,7 @@ struct SmemMS {
 template <int SPL, int ENV, int MODE>
 __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_args A) {
   using C = CfgMS<SPL>;
-  constexpr int NS = C::NS, PARTS = C::PARTS, NPW = C::NPW, EPP = C::EPP, OPAD = C::OPAD;
-  constexpr int LROW = E + 4 * PARTS;                    // padded logit-key row (floats)
+  constexpr int NS = C::NS, TPG = C::TPG, GA = C::GA;
   constexpr int CW = (ENV == CO_ENV_TSP ? 5 : 4) * E;
   constexpr int CUR_BLK = (ENV == CO_ENV_TSP ? 4 : 3);
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
@@ -65,8 +69,10 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
   const int B_traj = B_inst * S;
   const bool forced_start = (A.flags & CO_ROLLOUT_FORCED_START) != 0;
   const bool philox = (A.noise == nullptr);
-  const int nL = h * NPW + lane / PARTS;
-  const int part = lane % PARTS;
+  const int nL = tid % NS;            // selection phase: node of this thread ...
+  const int grp = tid / NS;           // ... and its group: trajectories grp * TPG .. grp * TPG + TPG - 1 of the pass
+  const bool sel_on = grp < GA;
+  const int wsel = (tid % NS) >> 5;   // warp index inside the selection group
   const float clip = A.tanh_clipping, inv_temp = 1.0f / A.temperature;
   const float Zb = clip * inv_temp;
 
@@ -101,8 +107,7 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
         lv = __ldg(reinterpret_cast<const float4*>(crow + (size_t)n * CW + 2 * E) + c);
       }
       reinterpret_cast<float4*>(sm.ptab + n * E)[c] = pv;
-      const int e = 4 * c;  // channel -> padded position: part chunk e / EPP shifted by 4 floats each
-      *reinterpret_cast<float4*>(sm.lkey + n * LROW + e + 4 * (e / EPP)) = lv;
+      sm.lkh[((c >> 2) * 4 + (c & 3)) * NS + n] = lv;  // chunk c = channels 4c..4c+3 = head c / 4, head chunk c % 4
     }
     if (tid < E) {
       sm.ptab[NS * E + tid] = 0.f;
@@ -244,6 +249,7 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
         // instruction streams hide the REDUX / MUFU / shuffle / LDS latencies of each chain.
         // Finished trajectories are computed too (their results are discarded by predication).
         // ---------------- glimpse (warp h = head h), two trajectories at a time (two transpose tiles)
+        float rinv[Q];  // 1 / sum(exp) of this head per trajectory: applied to the head's logit shares
 #pragma unroll
         for (int jp = 0; jp < Q; jp += 2) {
           float sc[2][SPL], m[2], esum[2];
@@ -324,73 +330,91 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
             r2[u] = (s0 + s1) + (s2 + s3);
           }
           const float x0 = __shfl_xor_sync(FULL, r2[0], 16), x1 = __shfl_xor_sync(FULL, r2[1], 16);
-          if (lane < 16) {
-            const int e = h * D + d;
-            sm.o[jp][e + 4 * (e / EPP)] = __fdividef(r2[0] + x0, esum[0]);
-            sm.o[jp + 1][e + 4 * (e / EPP)] = __fdividef(r2[1] + x1, esum[1]);
+          if (lane < 16) {  // un-normalised head outputs (d == lane here)
+            sm.oh[h][jp][d] = r2[0] + x0;
+            sm.oh[h][jp + 1][d] = r2[1] + x1;
           }
-          __syncwarp();  // the two tiles are reused by the next pair
+          rinv[jp] = __fdividef(1.0f, esum[0]);
+          rinv[jp + 1] = __fdividef(1.0f, esum[1]);
+          __syncwarp();  // the two tiles are reused by the next pair; oh is complete after the last pair
         }
-        __syncthreads();  // B1: heads of all trajectories complete
-
-        // ---------------- pointer logits: thread (nL, part); logit key streamed once for the Q queries
-        float z[Q];
+        // ---------------- head h's share of every pointer logit, for the Q trajectories: the head's slice of the folded
+        // logit key is read once per pass (conflict-free LDS.128, lane l = node l + 32 k), the head outputs as broadcasts
         {
-          float2 pa[Q], pb[Q];
+          float2 pl2[Q][SPL];
 #pragma unroll
-          for (int j = 0; j < Q; ++j) { pa[j] = make_float2(0.f, 0.f); pb[j] = make_float2(0.f, 0.f); }
-          const float4* lk = reinterpret_cast<const float4*>(sm.lkey + nL * LROW + part * (EPP + 4));
+          for (int j = 0; j < Q; ++j)
 #pragma unroll
-          for (int c = 0; c < EPP / 4; ++c) {
-            const float4 l4 = lk[c];
+            for (int k = 0; k < SPL; ++k) pl2[j][k] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 l4[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) l4[k] = sm.lkh[(h * 4 + c) * NS + lane + 32 * k];
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
-              const float4 x = reinterpret_cast<const float4*>(sm.o[j] + part * OPAD)[c];
-              pa[j] = ffma2(make_float2(x.x, x.y), make_float2(l4.x, l4.y), pa[j]);
-              pb[j] = ffma2(make_float2(x.z, x.w), make_float2(l4.z, l4.w), pb[j]);
-            }
-          }
-          float pl[Q], keyf[Q], ex[Q];
+              const float4 x = reinterpret_cast<const float4*>(sm.oh[h][j])[c];
 #pragma unroll
-          for (int j = 0; j < Q; ++j) pl[j] = (pa[j].x + pa[j].y) + (pb[j].x + pb[j].y);
-#pragma unroll
-          for (int off = PARTS / 2; off > 0; off >>= 1) {
-#pragma unroll
-            for (int j = 0; j < Q; ++j) pl[j] += __shfl_xor_sync(FULL, pl[j], off);
-          }
-#pragma unroll
-          for (int j = 0; j < Q; ++j) {
-            const bool fzL = feasible<ENV>(nL, (mybits[j] >> 8) & 1u, dL, used[j], thr, cur[j], anyfeas[j]);
-            const float lg = tanhf(pl[j] * 0.08838834764831845f) * clip;
-            z[j] = fzL ? lg * inv_temp : -INFINITY;
-            keyf[j] = z[j];
-            if (MODE == CO_MODE_SAMPLE) {
-              keyf[j] = -INFINITY;
-              if (part == 0 && fzL) {
-                const int traj = (g0 + j) * B_inst + b;
-                const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstep[j], nL)
-                                       : A.noise[((size_t)dstep[j] * B_traj + (traj < B_traj ? traj : 0)) * N + nL];
-                keyf[j] = z[j] - logf(q);
+              for (int k = 0; k < SPL; ++k) {
+                pl2[j][k] = ffma2(make_float2(x.x, x.y), make_float2(l4[k].x, l4[k].y), pl2[j][k]);
+                pl2[j][k] = ffma2(make_float2(x.z, x.w), make_float2(l4[k].z, l4[k].w), pl2[j][k]);
               }
             }
-            ex[j] = (part == 0) ? ex2((z[j] - Zb) * LOG2E) : 0.f;
           }
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {  // the Q partial sums, level by level
+          for (int j = 0; j < Q; ++j)
 #pragma unroll
-            for (int j = 0; j < Q; ++j) ex[j] += __shfl_xor_sync(FULL, ex[j], off);
+            for (int k = 0; k < SPL; ++k) sm.part[j][h][lane + 32 * k] = (pl2[j][k].x + pl2[j][k].y) * rinv[j];
+        }
+        __syncthreads();  // B1: every head's share of every logit of all trajectories is in shared memory
+
+        // ---------------- selection: thread (node nL, group grp) handles trajectories grp * TPG + jj
+        float z[TPG];
+        if (sel_on) {
+          float keyf[TPG], ex[TPG];
+#pragma unroll
+          for (int jj = 0; jj < TPG; ++jj) {
+            const int j = grp * TPG + jj;
+            const float pl = ((sm.part[j][0][nL] + sm.part[j][1][nL]) + (sm.part[j][2][nL] + sm.part[j][3][nL])) +
+                             ((sm.part[j][4][nL] + sm.part[j][5][nL]) + (sm.part[j][6][nL] + sm.part[j][7][nL]));
+            // the per-trajectory state of every trajectory is replicated in all threads: index it with a compile-time
+            // loop so that it stays in registers
+            uint32_t mb = 0; float usedj = 0.f; int curj = 0; bool anyj = false; int dstepj = 0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+              if (q == j) { mb = mybits[q]; usedj = used[q]; curj = cur[q]; anyj = anyfeas[q]; dstepj = dstep[q]; }
+            const bool fzL = feasible<ENV>(nL, (mb >> 8) & 1u, dL, usedj, thr, curj, anyj);
+            const float lg = tanhf(pl * 0.08838834764831845f) * clip;
+            z[jj] = fzL ? lg * inv_temp : -INFINITY;
+            keyf[jj] = z[jj];
+            if (MODE == CO_MODE_SAMPLE) {
+              keyf[jj] = -INFINITY;
+              if (fzL) {
+                const int traj = (g0 + j) * B_inst + b;
+                const float q = philox ? philox_exp1(A.seed, A.offset, traj, dstepj, nL)
+                                       : A.noise[((size_t)dstepj * B_traj + (traj < B_traj ? traj : 0)) * N + nL];
+                keyf[jj] = z[jj] - logf(q);
+              }
+            }
+            ex[jj] = ex2((z[jj] - Zb) * LOG2E);
           }
-          unsigned wkey[Q], vote[Q];
 #pragma unroll
-          for (int j = 0; j < Q; ++j) wkey[j] = __reduce_max_sync(FULL, fkey(keyf[j]));
+          for (int off = 16; off > 0; off >>= 1) {  // the partial sums, level by level
 #pragma unroll
-          for (int j = 0; j < Q; ++j) vote[j] = __ballot_sync(FULL, fkey(keyf[j]) == wkey[j]);
+            for (int jj = 0; jj < TPG; ++jj) ex[jj] += __shfl_xor_sync(FULL, ex[jj], off);
+          }
+          unsigned wkey[TPG], vote[TPG];
+#pragma unroll
+          for (int jj = 0; jj < TPG; ++jj) wkey[jj] = __reduce_max_sync(FULL, fkey(keyf[jj]));
+#pragma unroll
+          for (int jj = 0; jj < TPG; ++jj) vote[jj] = __ballot_sync(FULL, fkey(keyf[jj]) == wkey[jj]);
           if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
-              sm.red_key[j][h] = wkey[j];
-              sm.red_idx[j][h] = h * NPW + (__ffs(vote[j]) - 1) / PARTS;
-              sm.red_sum[j][h] = ex[j];
+            for (int jj = 0; jj < TPG; ++jj) {
+              const int j = grp * TPG + jj;
+              sm.red_key[j][wsel] = wkey[jj];
+              sm.red_idx[j][wsel] = 32 * wsel + __ffs(vote[jj]) - 1;
+              sm.red_sum[j][wsel] = ex[jj];
             }
           }
         }
@@ -401,19 +425,17 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
           const int traj = (g0 + j) * B_inst + b;
           int a;
           float Ssum;
-          {
-            const uint4 k0 = reinterpret_cast<const uint4*>(sm.red_key[j])[0], k1 = reinterpret_cast<const uint4*>(sm.red_key[j])[1];
-            const int4 i0 = reinterpret_cast<const int4*>(sm.red_idx[j])[0], i1 = reinterpret_cast<const int4*>(sm.red_idx[j])[1];
-            const float4 u0 = reinterpret_cast<const float4*>(sm.red_sum[j])[0], u1 = reinterpret_cast<const float4*>(sm.red_sum[j])[1];
-            Ssum = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
-            unsigned bk = k0.x; a = i0.x;
-            if (k0.y > bk) { bk = k0.y; a = i0.y; }
-            if (k0.z > bk) { bk = k0.z; a = i0.z; }
-            if (k0.w > bk) { bk = k0.w; a = i0.w; }
-            if (k1.x > bk) { bk = k1.x; a = i1.x; }
-            if (k1.y > bk) { bk = k1.y; a = i1.y; }
-            if (k1.z > bk) { bk = k1.z; a = i1.z; }
-            if (k1.w > bk) { bk = k1.w; a = i1.w; }
+          {  // SPL selection warps per trajectory; entries beyond SPL are never written nor read
+            const uint4 k0 = *reinterpret_cast<const uint4*>(sm.red_key[j]);
+            const int4 i0 = *reinterpret_cast<const int4*>(sm.red_idx[j]);
+            const float4 u0 = *reinterpret_cast<const float4*>(sm.red_sum[j]);
+            unsigned bk = k0.x; a = i0.x; Ssum = u0.x;  // strict '>' keeps the lowest warp (= lowest node) on ties
+            if (SPL >= 2) { Ssum += u0.y; if (k0.y > bk) { bk = k0.y; a = i0.y; } }
+            if (SPL >= 4) {
+              Ssum = (u0.x + u0.y) + (u0.z + u0.w);
+              if (k0.z > bk) { bk = k0.z; a = i0.z; }
+              if (k0.w > bk) { bk = k0.w; a = i0.w; }
+            }
           }
           if (!fin[j]) {  // uniform across the block: the state is replicated
             const int t = tstep[j];
@@ -421,8 +443,8 @@ __global__ void __launch_bounds__(256, 1) rollout_ms_kernel(const co_rollout_arg
               const int forced = (int)A.forced_actions[(size_t)traj * T_max + t];
               a = (forced < 0 || forced >= N) ? 0 : forced;
             }
-            if (nL == a && part == 0) {
-              const float lpL = (z[j] - Zb) - lg2(Ssum) * LN2;
+            if (sel_on && nL == a && j / TPG == grp) {
+              const float lpL = (z[j % TPG] - Zb) - lg2(Ssum) * LN2;
               A.logp_out[(size_t)traj * T_max + t] = lpL;
               sm.ll_acc[j] += lpL;
             }
