@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       int pend_a = -1;              // sdvrp: demand write-back deferred past the next barrier (see env_step)
       float pend_d = 0.f, FKW = 0.f;
       float ll = 0.f;               // log-likelihood, accumulated by lane 0 of the log-prob warp
+      // sdvrp serves demand in place (sm.dem): every further trajectory of the instance starts from the original demands
+      // (every thread is past the previous trajectory's last read: the epilogue barrier)
+      if (SD && s > 0 && tid < NS) sm.dem[tid] = (tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
       __syncthreads();  // previous trajectory finished with qfix
       if (tid < E) {
         float g = A.graph_ctx ? A.graph_ctx[(size_t)b * E + tid] : 0.f;

@@ -226,3 +226,27 @@ def test_sdvrp_fused_equals_stepping_and_multisample():
         s3 = pol(td, env, phase="train", decode_type="sampling", seed=5)
     assert torch.equal(s1["actions"], s2["actions"]) and not torch.equal(s1["actions"], s3["actions"])
     assert torch.isfinite(s1["log_likelihood"]).all() and (s1["log_likelihood"] < 0).all()
+
+
+@pytest.mark.gpu
+def test_sdvrp_multistart_trajectories_share_an_instance():
+    """S > 1 trajectories of one instance inside the persistent kernel: split deliveries consume the demand in place, so
+    every further trajectory must start from the original demands again -- valid tours for every start
+    (check_solution=True) and the same trajectories as the stepping kernels (sdvrp/env.py:55-116, ops.py:128-149)."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(11)
+    for n, starts in ((20, 3), (50, 5)):
+        env = get_env("sdvrp", generator_params=dict(num_loc=n), check_solution=True)
+        pol = FusedAttentionModelPolicy(env_name="sdvrp", num_encoder_layers=1).to(DEV).eval()
+        pol.decoder.cache_gemm = "cublas"
+        with torch.inference_mode():
+            td = env.reset(env.generator(64).to(DEV))
+            a = pol(td, env, phase="test", decode_type="multistart_greedy", num_starts=starts)
+            b = pol(td, env, phase="test", decode_type="multistart_greedy", num_starts=starts, fused_rollout=False)
+        T = min(a["actions"].shape[1], b["actions"].shape[1])
+        same = (a["actions"][:, :T] == b["actions"][:, :T]).all(1)
+        assert same.float().mean() >= 0.9
+        torch.testing.assert_close(a["reward"][same], b["reward"][same], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(a["log_likelihood"][same], b["log_likelihood"][same], rtol=RTOL, atol=ATOL_LP * 3)

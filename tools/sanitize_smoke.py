@@ -8,7 +8,7 @@ from rl4co_b200.policy import FusedAttentionModelPolicy
 from rl4co_b200.reinforce import pomo_step
 
 dev = torch.device("cuda:0")
-CASES = (("tsp", 20), ("cvrp", 20), ("tsp", 50), ("cvrp", 100), ("tsp", 100))
+CASES = (("tsp", 20), ("cvrp", 20), ("sdvrp", 20), ("tsp", 50), ("cvrp", 100), ("tsp", 100))
 if os.environ.get("SAN_ONLY"):
     CASES = tuple(c for c in CASES if c[0] == os.environ["SAN_ONLY"])
 for env_name, n in CASES:
@@ -31,3 +31,17 @@ hi, lo = native.split_tf32(w)
 native.gemm_tf32x3(a, hi, lo, residual=torch.randn(300, 128, device=dev))
 torch.cuda.synchronize()
 print("gemm ok")
+# training-step attention kernels (forward, dQ, dK/dV) with a mask and strided key / value views; instance norm
+from rl4co_b200 import attention_train as AT
+
+torch.manual_seed(1)
+q = torch.randn(6, 131, 128, device=dev, requires_grad=True)
+cache = torch.randn(6, 101, 512, device=dev, requires_grad=True)
+mask = torch.rand(6, 131, 101, device=dev) < 0.5
+mask[..., 0] = True
+AT.attention(q, cache[..., :128], cache[..., 128:256], mask).square().sum().backward()
+qkv = torch.randn(5, 100, 384, device=dev, requires_grad=True)
+AT.self_attention_packed(qkv).sum().backward()
+native.instance_norm(torch.randn(9, 100, 128, device=dev), torch.ones(128, device=dev), torch.zeros(128, device=dev))
+torch.cuda.synchronize()
+print("attention / norm ok")
