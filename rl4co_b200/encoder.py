@@ -11,9 +11,12 @@ with the reference's module tree so that a reference ``state_dict`` loads unchan
 It runs once per instance.  Inference (no autograd, eval mode, CUDA): every nn.Linear runs on the
 hand-written tcgen05 3xTF32 GEMM (`co_gemm_tf32x3`; bias / ReLU / skip connection / eval-mode
 BatchNorm folded into its epilogue) and the attention core on `co_encoder_mha` (tcgen05 scores
-and P.V for N > 64) -- `_net_fused` below.  Still stock torch ops there: the K = 2 / 3 init
-embedding, the graph-context mean + Linear of the decoder, and instance normalisation.  Under
-autograd (training) the stock modules (cuBLAS / SDPA) run, because the kernels are forward-only.
+and P.V for N > 64), the FFN block on `co_ffn_fused`, instance normalisation on `co_instance_norm`
+-- `_net_fused` below.  Still stock torch ops there: the K = 2 / 3 init embedding and the
+graph-context mean + Linear of the decoder.  Under autograd (training) the stock Linear / norm modules
+run (cuBLAS), with the attention core on the hand-written forward / backward kernels
+(`co_attn_fwd` / `co_attn_bwd`, attention_train.py); without a graph but in train mode (batch
+statistics) the attention core runs on `co_encoder_mha`.
 """
 
 from __future__ import annotations
