@@ -12,8 +12,6 @@ fallback inside this module; callers decide (shape limits: 8 heads x 16, keys <=
 
 from __future__ import annotations
 
-import math
-
 import torch
 
 from . import native
@@ -104,5 +102,3 @@ def self_attention_packed(qkv):
     """qkv [B, N, 3E] (contiguous) -> [B, N, E]; N <= 128."""
     return _SelfAttentionPacked.apply(qkv.contiguous())
 
-
-SCALE = 1.0 / math.sqrt(E // H)
