@@ -95,6 +95,18 @@ int co_sdvrp_step(const int64_t* action, const float* demand_in, float* demand_o
                   const float* vehicle_capacity, const float* used_in, float* used_out,
                   int64_t* current_node, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream);
 
+/* OPEnv (rl4co/envs/routing/op/env.py; sibling env, orienteering): locs [B,N,2] with the depot at 0, prize [B,N] (depot 0),
+ * max_length [B,N] (per node: the budget minus the way back to the depot, env.py:121-123), visited [B,N] bool,
+ * tour_length / current_total_prize [B] f32, current_node / i [B] i64 (updated in place by co_op_step).
+ * co_op_step = _step :72-105 + get_action_mask :140-155 (done = depot re-entered after step 0);
+ * co_op_reward = _get_reward :157-165 (sum of the collected prizes over actions [B,T]). */
+int co_op_action_mask(const float* locs, const float* max_length, const uint8_t* visited, const float* tour_length,
+                      const int64_t* current_node, uint8_t* mask_out, int B, int N, void* stream);
+int co_op_step(const int64_t* action, const float* locs, const float* prize, const float* max_length,
+               const uint8_t* visited_in, uint8_t* visited_out, float* tour_length, float* current_total_prize,
+               int64_t* current_node, int64_t* i, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream);
+int co_op_reward(const float* prize, const int64_t* actions, float* reward, int B, int N, int T, void* stream);
+
 int co_tour_length(const float* locs, const int64_t* actions, float* reward, int B,
                    int B_locs, int N, int T, int with_depot, void* stream);
 

@@ -289,8 +289,78 @@ def sdvrp_dynamic_embedding(weights, st):
     return F.linear(d, _w(weights, "dynamic_embedding.projection.weight")).chunk(3, dim=-1)
 
 
-ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset, "sdvrp": sdvrp_reset}
-ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step, "sdvrp": sdvrp_step}
+# reference: rl4co/envs/routing/op/env.py (orienteering: collect prizes, return to the depot within max_length)
+
+
+def op_action_mask(st):
+    """op/env.py:140-155: visited, or the depot already re-entered, or tour_length + dist(cur, n) > max_length[n]
+    (max_length[n] already has the way back to the depot taken off, op/env.py:121-123); the depot is always feasible"""
+    current_loc = gather_by_index(st["locs"], st["current_node"])[..., None, :]
+    exceeds_length = st["tour_length"][..., None] + (st["locs"] - current_loc).norm(p=2, dim=-1) > st["max_length"]
+    mask = st["visited"] | st["visited"][..., 0:1] | exceeds_length
+    action_mask = ~mask
+    action_mask[..., 0] = 1
+    return action_mask
+
+
+def op_reset(depot, locs, prize, max_length):
+    """op/env.py:107-138"""
+    B = locs.shape[0]
+    dev = locs.device
+    locs_with_depot = torch.cat((depot[:, None, :], locs), -2)
+    st = {
+        "locs": locs_with_depot,
+        "prize": F.pad(prize, (1, 0), mode="constant", value=0),
+        "tour_length": torch.zeros(B, device=dev),
+        "max_length": max_length[..., None] - (depot[..., None, :] - locs_with_depot).norm(p=2, dim=-1) - 1e-6,
+        "current_node": torch.zeros(B, 1, dtype=torch.long, device=dev),
+        "visited": torch.zeros((B, locs_with_depot.shape[-2]), dtype=torch.bool, device=dev),
+        "current_total_prize": torch.zeros(B, dtype=torch.float, device=dev),
+        "i": torch.zeros((B,), dtype=torch.int64, device=dev),
+    }
+    st["action_mask"] = op_action_mask(st)
+    st["done"] = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+    return st
+
+
+def op_step(state, action):
+    """op/env.py:72-105: done when the depot is re-entered after step 0"""
+    st = dict(state)
+    current_node = action[:, None]
+    previous_loc = gather_by_index(st["locs"], st["current_node"])
+    current_loc = gather_by_index(st["locs"], current_node)
+    tour_length = st["tour_length"] + (current_loc - previous_loc).norm(p=2, dim=-1)
+    current_total_prize = st["current_total_prize"] + gather_by_index(st["prize"], current_node, dim=-1)
+    visited = st["visited"].scatter(-1, current_node, 1)
+    done = (current_node.squeeze(-1) == 0) & (st["i"] > 0)
+    st.update(tour_length=tour_length, current_node=current_node, visited=visited,
+              current_total_prize=current_total_prize, i=st["i"] + 1, reward=torch.zeros_like(done), done=done,
+              action=action)
+    st["action_mask"] = op_action_mask(st)
+    return st
+
+
+def op_reward(st, actions):
+    """op/env.py:157-165: sum of the collected prizes (the depot's is 0)"""
+    if actions.size(-1) == 1:
+        assert (actions == 0).all(), "If all length 1 tours, they should be zero"
+        return torch.zeros(actions.size(0), dtype=torch.float, device=actions.device)
+    return st["prize"].gather(1, actions).sum(-1)
+
+
+def op_check_solution(st, actions, add_distance_to_depot: bool = True):
+    """op/env.py:167-192"""
+    sorted_actions = actions.sort(1)[0]
+    assert ((sorted_actions[:, 1:] == 0) | (sorted_actions[:, 1:] > sorted_actions[:, :-1])).all(), "Duplicates"
+    length = get_tour_length(gather_by_index(st["locs"], actions))
+    max_length = st["max_length"]
+    if add_distance_to_depot:
+        max_length = max_length + (st["locs"][..., 0:1, :] - st["locs"]).norm(p=2, dim=-1) + 1e-6
+    assert (length[..., None] <= max_length + 1e-5).all(), "Max length exceeded"
+
+
+ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset, "sdvrp": sdvrp_reset, "op": op_reset}
+ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step, "sdvrp": sdvrp_step, "op": op_step}
 
 
 def env_reset(env_name, inst):
@@ -299,16 +369,21 @@ def env_reset(env_name, inst):
         return tsp_reset(inst["locs"])
     if env_name == "sdvrp":
         return sdvrp_reset(inst["depot"], inst["locs"], inst["demand"])
+    if env_name == "op":
+        return op_reset(inst["depot"], inst["locs"], inst["prize"], inst["max_length"])
     return cvrp_reset(inst["depot"], inst["locs"], inst["demand"])
 
 
 def env_reward(env_name, st, actions):
+    if env_name == "op":
+        return op_reward(st, actions)
     return tsp_reward(st["locs"], actions) if env_name == "tsp" else cvrp_reward(st["locs"], actions)
 
 
 # --------------------------------------------------------------------------- generators
 # reference: rl4co/envs/routing/tsp/generator.py:49-58, cvrp/generator.py:15-30,114-140
 
+OP_MAX_LENGTHS = {20: 2.0, 50: 3.0, 100: 4.0}  # op/generator.py:16
 CAPACITIES = {10: 20.0, 15: 25.0, 20: 30.0, 30: 33.0, 40: 37.0, 50: 40.0, 60: 43.0, 75: 45.0,
               100: 50.0, 125: 55.0, 150: 60.0, 200: 70.0, 500: 100.0, 1000: 150.0}
 
@@ -321,6 +396,12 @@ def generate_instances(env_name, batch, num_loc, generator=None):
 
     if env_name == "tsp":
         return {"locs": uni((batch, num_loc, 2), 0.0, 1.0)}
+    if env_name == "op":  # op/generator.py:102-139, prize_type "dist": prize from the distance to the depot
+        locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
+        prize = (locs[..., 0:1, :] - locs[..., 1:, :]).norm(p=2, dim=-1)
+        prize = (1 + (prize / prize.max(dim=-1, keepdim=True)[0] * 99).int()).float() / 100
+        ml = OP_MAX_LENGTHS.get(num_loc) or OP_MAX_LENGTHS[min(OP_MAX_LENGTHS, key=lambda x: abs(x - num_loc))]
+        return {"locs": locs[:, 1:, :], "depot": locs[:, 0, :], "prize": prize, "max_length": torch.full((batch,), ml)}
     # cvrp and sdvrp share CVRPGenerator (sdvrp/env.py:47-54)
     locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
     demand = uni((batch, num_loc), 0.0, 9.0)
@@ -367,6 +448,13 @@ def vrp_context(weights, emb, st):
     return F.linear(torch.cat([cur, state_emb], -1), _w(weights, "context_embedding.project_context.weight"))
 
 
+def op_context(weights, emb, st):
+    """nn/env_embeddings/context.py:61-74,201-213 (EnvContext.forward + OPContext): [h_cur ; max_length[0] - tour_length]"""
+    cur = gather_by_index(emb, st["current_node"])
+    state_emb = (st["max_length"][..., 0] - st["tour_length"])[..., None]
+    return F.linear(torch.cat([cur, state_emb], -1), _w(weights, "context_embedding.project_context.weight"))
+
+
 def pointer_logits(weights, q, K, V, L, mask, num_heads=8):
     """nn/attention.py:274-320 (PointerAttention.forward, mask_inner=True, no out bias)"""
     def heads(x):  # "... g (h s) -> ... h g s"
@@ -390,7 +478,8 @@ def decoder_forward(weights, env_name, st, cache, num_starts=0, faithful_copies=
     two_batch_dims = st["action_mask"].dim() == 3
     if two_batch_dims and isinstance(g, torch.Tensor):
         g = g.unsqueeze(1)
-    ctx = tsp_context(weights, emb, st) if env_name == "tsp" else vrp_context(weights, emb, st)  # cvrp, sdvrp
+    ctx = (tsp_context(weights, emb, st) if env_name == "tsp" else
+           op_context(weights, emb, st) if env_name == "op" else vrp_context(weights, emb, st))  # cvrp, sdvrp
     q = ctx + g
     q = q.unsqueeze(1) if q.ndim == 2 else q
     K, V, L = cache["glimpse_key"], cache["glimpse_val"], cache["logit_key"]
@@ -624,8 +713,8 @@ def init_embedding(weights, env_name, st):
         return F.linear(st["locs"], weights[p + "init_embed.weight"], weights[p + "init_embed.bias"])
     depot, cities = st["locs"][:, :1, :], st["locs"][:, 1:, :]
     de = F.linear(depot, weights[p + "init_embed_depot.weight"], weights[p + "init_embed_depot.bias"])
-    ne = F.linear(torch.cat((cities, st["demand"][..., None]), -1), weights[p + "init_embed.weight"],
-                  weights[p + "init_embed.bias"])
+    feat = st["prize"][..., 1:, None] if env_name == "op" else st["demand"][..., None]  # init.py:254-280 / 115-136
+    ne = F.linear(torch.cat((cities, feat), -1), weights[p + "init_embed.weight"], weights[p + "init_embed.bias"])
     return torch.cat((de, ne), -2)
 
 

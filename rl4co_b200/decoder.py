@@ -265,9 +265,11 @@ class FusedAttentionModelDecoder(nn.Module):
                 feat[:, 0] = 0
                 w._keepalive.append(feat)
                 w.dynamic_feature = feat.data_ptr()
+            if self.env_name == "op":  # OPContext (context.py:201-213): [h_cur ; max_length[..., 0] - tour_length]
+                spent, budget = td["tour_length"].reshape(-1).contiguous(), td["max_length"][..., 0].reshape(-1).contiguous()
+            else:                      # VRPContext (context.py:137-149): [h_cur ; vehicle_capacity - used_capacity]
+                spent, budget = td["used_capacity"].reshape(-1).contiguous(), td["vehicle_capacity"].reshape(-1).contiguous()
             logits = native.pointer_logits(
                 self.env_name, w, cached.node_embeddings.contiguous(), cached.graph_context_or_none, cached.glimpse_key,
-                cached.glimpse_val, cached.logit_key_folded, mask, None, cur, None,
-                td["used_capacity"].reshape(-1).contiguous(), td["vehicle_capacity"].reshape(-1).contiguous(),
-                B_traj, B_inst, N)
+                cached.glimpse_val, cached.logit_key_folded, mask, None, cur, None, spent, budget, B_traj, B_inst, N)
         return logits, mask

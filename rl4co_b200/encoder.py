@@ -44,8 +44,20 @@ class VRPInitEmbedding(nn.Module):
     def forward(self, td):
         depot, cities = td["locs"][:, :1, :], td["locs"][:, 1:, :]
         depot_embedding = self.init_embed_depot(depot)
-        node_embeddings = self.init_embed(torch.cat((cities, td["demand"][..., None]), -1))
+        node_embeddings = self.init_embed(torch.cat((cities, self._node_feature(td)), -1))
         return torch.cat((depot_embedding, node_embeddings), -2)
+
+    @staticmethod
+    def _node_feature(td):
+        return td["demand"][..., None]
+
+
+class OPInitEmbedding(VRPInitEmbedding):
+    """init.py:254-280: depot (x, y); customers (x, y, prize) -- the module tree of VRPInitEmbedding."""
+
+    @staticmethod
+    def _node_feature(td):
+        return td["prize"][..., 1:, None]  # the depot's entry is excluded
 
 
 def _train_attention_on(x, n_keys: int, num_heads: int) -> bool:
@@ -145,7 +157,8 @@ class AttentionModelEncoder(nn.Module):
         env_name = getattr(env_name, "name", env_name)
         self.env_name = env_name
         if init_embedding is None:
-            init_embedding = {"tsp": TSPInitEmbedding, "cvrp": VRPInitEmbedding, "sdvrp": VRPInitEmbedding}[env_name](embed_dim)
+            init_embedding = {"tsp": TSPInitEmbedding, "cvrp": VRPInitEmbedding, "sdvrp": VRPInitEmbedding,
+                              "op": OPInitEmbedding}[env_name](embed_dim)
         self.init_embedding = init_embedding
         self.net = GraphAttentionNetwork(num_heads, embed_dim, num_layers, normalization, feedforward_hidden) \
             if net is None else net

@@ -110,6 +110,47 @@ class CVRPGenerator(Generator, _DeviceStream):
         )
 
 
+OP_MAX_LENGTHS = {20: 2.0, 50: 3.0, 100: 4.0}  # rl4co/envs/routing/op/generator.py:14
+
+
+class OPGenerator(Generator, _DeviceStream):
+    """rl4co/envs/routing/op/generator.py:19-139: uniform locations (depot = first sampled point); prize by type --
+    "dist" (default, Fischetti et al. / Kool et al.: from the distance to the depot), "unif", "const"; max_length from
+    the size table.  `device="cuda"`: locations from co_generate_uniform, prizes derived on the device."""
+
+    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, prize_type: str = "dist",
+                 max_length: float | None = None, device=None, seed=None, **_):
+        self._init_stream(device, seed)
+        self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
+        if prize_type not in ("dist", "unif", "const"):
+            raise ValueError(f"Invalid prize_type: {prize_type}")
+        self.prize_type = prize_type
+        if max_length is None:
+            max_length = OP_MAX_LENGTHS.get(num_loc) or OP_MAX_LENGTHS[min(OP_MAX_LENGTHS, key=lambda x: abs(x - num_loc))]
+        self.max_length = max_length
+
+    def _generate(self, batch_size) -> TensorDict:
+        dev = self.device if self.on_device else None
+        if self.on_device:
+            locs = native.generate_uniform((*batch_size, self.num_loc + 1, 2), self.device, self.seed,
+                                           self._next_offset(2), self.min_loc, self.max_loc)
+        else:
+            locs = torch.rand(*batch_size, self.num_loc + 1, 2) * (self.max_loc - self.min_loc) + self.min_loc
+        if self.prize_type == "const":
+            prize = torch.ones(*batch_size, self.num_loc, device=dev)
+        elif self.prize_type == "unif":
+            prize = (1 + torch.randint(0, 100, (*batch_size, self.num_loc), device=dev).float()) / 100
+        else:
+            prize = (locs[..., 0:1, :] - locs[..., 1:, :]).norm(p=2, dim=-1)
+            prize = (1 + (prize / prize.max(dim=-1, keepdim=True)[0] * 99).int()).float() / 100
+        if isinstance(self.max_length, torch.Tensor):
+            max_length = self.max_length
+        else:
+            max_length = torch.full((*batch_size,), self.max_length, device=dev)
+        return TensorDict({"locs": locs[..., 1:, :], "depot": locs[..., 0, :], "prize": prize, "max_length": max_length},
+                          batch_size=batch_size, device=dev)
+
+
 class FusedEnvBase:
     """Host-side mirror of RL4COEnvBase (rl4co/envs/common/base.py:19-333)."""
 
@@ -438,7 +479,98 @@ class FusedSDVRPEnv(FusedCVRPEnv):
         assert (demands == 0).all(), "All demand must be satisfied"
 
 
-ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv, "sdvrp": FusedSDVRPEnv}
+class FusedOPEnv(FusedEnvBase):
+    """CUDA drop-in for rl4co.envs.OPEnv (rl4co/envs/routing/op/env.py:18-242, orienteering): collect prizes and be
+    back at the depot within `max_length`.  State keys / dtypes as the reference's: `locs` [B,N,2] (depot at 0), `prize`
+    [B,N] (depot 0), `tour_length` [B], `max_length` [B,N] (budget minus the way back per node), `current_node` [B,1],
+    `visited` bool [B,N], `current_total_prize` [B], `i` [B].  Runs on the stepping kernels (co_op_step /
+    co_op_action_mask / co_op_reward; the decoder shares the capacity-context arithmetic of co_pointer_logits)."""
+
+    name = "op"
+
+    def __init__(self, generator=None, generator_params: dict | None = None, prize_type: str = "dist", **kwargs):
+        super().__init__(**kwargs)
+        if generator is None:
+            generator = OPGenerator(**{"prize_type": prize_type, **(generator_params or {})})
+        self.generator = generator
+        self.prize_type = prize_type
+
+    def _reset(self, td: TensorDict, batch_size=None) -> TensorDict:
+        """op/env.py:107-138"""
+        device = td.device
+        locs = torch.cat((td["depot"][:, None, :], td["locs"]), -2)
+        td_reset = TensorDict(
+            {
+                "locs": locs,
+                "prize": torch.nn.functional.pad(td["prize"], (1, 0), mode="constant", value=0),
+                "tour_length": torch.zeros(*batch_size, device=device),
+                "max_length": td["max_length"][..., None] - (td["depot"][..., None, :] - locs).norm(p=2, dim=-1) - 1e-6,
+                "current_node": torch.zeros(*batch_size, 1, dtype=torch.long, device=device),
+                "visited": torch.zeros((*batch_size, locs.shape[-2]), dtype=torch.bool, device=device),
+                "current_total_prize": torch.zeros(*batch_size, dtype=torch.float, device=device),
+                "i": torch.zeros((*batch_size,), dtype=torch.int64, device=device),
+            },
+            batch_size=batch_size,
+        )
+        if locs.is_cuda:
+            mask = self.get_action_mask(td_reset)
+        else:  # reset only allocates state: the initial mask of op/env.py:140-155 in torch
+            exceeds = (locs - locs[..., 0:1, :]).norm(p=2, dim=-1) > td_reset["max_length"]
+            mask = ~exceeds
+            mask[..., 0] = True
+        td_reset.set("action_mask", mask)
+        return td_reset
+
+    def _step(self, td: TensorDict) -> TensorDict:
+        """op/env.py:72-105 incl. the trailing get_action_mask, one kernel (co_op_step)."""
+        action = td["action"].contiguous()
+        B = action.shape[0]
+        vin = td["visited"].contiguous()
+        vout = vin if self.inplace else torch.empty_like(vin)
+        tour_length = td["tour_length"].clone()
+        prize_sum = td["current_total_prize"].clone()
+        current_node = td["current_node"].reshape(B).clone()
+        i = td["i"].clone()
+        done = torch.empty(B, dtype=torch.bool, device=action.device)
+        mask_out = torch.empty(vin.shape, dtype=torch.bool, device=action.device)
+        native.op_step(action, td["locs"].contiguous(), td["prize"].contiguous(), td["max_length"].contiguous(), vin, vout,
+                       tour_length, prize_sum, current_node, i, done, mask_out)
+        td.update({"tour_length": tour_length, "current_node": current_node[:, None], "visited": vout,
+                   "current_total_prize": prize_sum, "i": i, "reward": torch.zeros_like(done), "done": done})
+        td.set("action_mask", mask_out)
+        return td
+
+    @staticmethod
+    def get_action_mask(td: TensorDict) -> torch.Tensor:
+        """op/env.py:140-155 (co_op_action_mask)"""
+        visited = td["visited"].contiguous()
+        mask = torch.empty(visited.shape, dtype=torch.bool, device=visited.device)
+        return native.op_action_mask(td["locs"].contiguous(), td["max_length"].contiguous(), visited,
+                                     td["tour_length"].contiguous(), td["current_node"].reshape(-1).contiguous(), mask)
+
+    def _get_reward(self, td: TensorDict, actions: torch.Tensor) -> torch.Tensor:
+        """op/env.py:157-165 (co_op_reward)"""
+        if actions.size(-1) == 1:
+            assert (actions == 0).all(), "If all length 1 tours, they should be zero"
+            return torch.zeros(actions.size(0), dtype=torch.float, device=actions.device)
+        return native.op_reward(td["prize"].contiguous(), actions.contiguous())
+
+    @staticmethod
+    def check_solution_validity(td: TensorDict, actions: torch.Tensor, add_distance_to_depot: bool = True) -> None:
+        """op/env.py:167-192: no customer twice, length within the budget.  Validation path (host-synchronising
+        asserts like the reference)."""
+        sorted_actions = actions.sort(1)[0]
+        assert ((sorted_actions[:, 1:] == 0) | (sorted_actions[:, 1:] > sorted_actions[:, :-1])).all(), "Duplicates"
+        length = -native.tour_length(td["locs"].contiguous(), actions.contiguous(), with_depot=False)
+        max_length = td["max_length"]
+        if add_distance_to_depot:
+            max_length = max_length + (td["locs"][..., 0:1, :] - td["locs"]).norm(p=2, dim=-1) + 1e-6
+        if max_length.shape[0] != length.shape[0]:
+            max_length = max_length.repeat(length.shape[0] // max_length.shape[0], 1)
+        assert (length[..., None] <= max_length + 1e-5).all(), "Max length exceeded"
+
+
+ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv, "sdvrp": FusedSDVRPEnv, "op": FusedOPEnv}
 
 
 def _register_with_torchrl() -> bool:

@@ -22,13 +22,15 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
 SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
-           "ffn_fused.cu", "data_kernels.cu", "attn_train.cu", "norm_kernels.cu"]
+           "ffn_fused.cu", "data_kernels.cu", "attn_train.cu", "norm_kernels.cu", "op_kernels.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
 ENV_SDVRP = 2
-ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP}
+#: "op" shares the cvrp decoder arithmetic (context = [h_cur ; budget - spent], context.py:201-213): max_length[:, 0] and
+#: tour_length stand in for vehicle_capacity and used_capacity
+ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP, "op": ENV_CVRP}
 #: environments the whole-episode kernel (co_rollout) is instantiated for; others take the stepping kernels
 ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp")
 SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
@@ -40,7 +42,7 @@ EXPORTS = [
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
     "co_ffn_fused", "co_ffn_tile_weights", "co_ffn_tiled_weight_floats", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
-    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd", "co_instance_norm",
+    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd", "co_instance_norm", "co_op_step", "co_op_action_mask", "co_op_reward",
 ]
 
 
@@ -143,6 +145,9 @@ def lib() -> ctypes.CDLL:
     L.co_sdvrp_step.argtypes = [c_void_p] * 9 + [c_int, c_int, c_void_p]
     L.co_check_tours.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.co_op_action_mask.argtypes = [c_void_p] * 6 + [c_int, c_int, c_void_p]
+    L.co_op_step.argtypes = [c_void_p] * 12 + [c_int, c_int, c_void_p]
+    L.co_op_reward.argtypes = [c_void_p] * 3 + [c_int, c_int, c_int, c_void_p]
     L.co_instance_norm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_float, c_void_p]
     L.co_attn_fwd.argtypes = [POINTER(AttnArgs), c_void_p]
     L.co_attn_bwd.argtypes = [POINTER(AttnArgs), c_void_p]
@@ -279,6 +284,42 @@ def sdvrp_step(action, demand_in, demand_out, cap, used_in, used_out, current_no
                                _ptr(used_in, F32, "used_in"), _ptr(used_out, F32, "used_out"),
                                _ptr(current_node, I64, "current_node"), _bool_ptr(done, "done"),
                                _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_sdvrp_step")
+
+
+@_on_device_of_first_tensor
+def op_action_mask(locs, max_length, visited, tour_length, current_node, mask_out):
+    """co_op_action_mask (op/env.py:140-155)."""
+    B, N = mask_out.shape
+    _check(lib().co_op_action_mask(_ptr(locs, F32, "locs"), _ptr(max_length, F32, "max_length"), _bool_ptr(visited, "visited"),
+                                   _ptr(tour_length, F32, "tour_length"), _ptr(current_node, I64, "current_node"),
+                                   _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_op_action_mask")
+    return mask_out
+
+
+@_on_device_of_first_tensor
+def op_step(action, locs, prize, max_length, visited_in, visited_out, tour_length, current_total_prize, current_node, i,
+            done, mask_out):
+    """co_op_step (op/env.py:72-105 + get_action_mask): tour_length, current_total_prize, current_node, i in place."""
+    B, N = mask_out.shape
+    _check(lib().co_op_step(_ptr(action, I64, "action"), _ptr(locs, F32, "locs"), _ptr(prize, F32, "prize"),
+                            _ptr(max_length, F32, "max_length"), _bool_ptr(visited_in, "visited_in"),
+                            _bool_ptr(visited_out, "visited_out"), _ptr(tour_length, F32, "tour_length"),
+                            _ptr(current_total_prize, F32, "current_total_prize"), _ptr(current_node, I64, "current_node"),
+                            _ptr(i, I64, "i"), _bool_ptr(done, "done"), _bool_ptr(mask_out, "mask_out"), B, N, _stream()),
+           "co_op_step")
+
+
+@_on_device_of_first_tensor
+def op_reward(prize, actions):
+    """co_op_reward (op/env.py:157-165): prize [B_inst, N] (depot 0), actions [B, T] -> [B]; trajectory j uses instance
+    j % B_inst."""
+    B, T = actions.shape
+    if prize.shape[0] != B:
+        prize = prize.repeat(B // prize.shape[0], 1)
+    out = torch.empty(B, dtype=F32, device=actions.device)
+    _check(lib().co_op_reward(_ptr(prize.contiguous(), F32, "prize"), _ptr(actions, I64, "actions"), _ptr(out, F32, "reward"),
+                              B, prize.shape[1], T, _stream()), "co_op_reward")
+    return out
 
 
 @_on_device_of_first_tensor

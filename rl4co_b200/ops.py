@@ -56,9 +56,9 @@ def unbatchify_and_gather(x, idx, n: int):
 
 
 def get_num_starts(td, env_name=None) -> int:
-    """rl4co/utils/ops.py:115-125 (tsp / cvrp / sdvrp rows)"""
+    """rl4co/utils/ops.py:115-125 (tsp / cvrp / sdvrp / op rows)"""
     num_starts = td["action_mask"].shape[-1]
-    if env_name in ("cvrp", "sdvrp"):
+    if env_name in ("cvrp", "sdvrp", "op"):
         num_starts -= 1
     return num_starts
 
@@ -67,7 +67,14 @@ def select_start_nodes(td, env, num_starts: int):
     """rl4co/utils/ops.py:128-149 (tsp / depot-env rows)"""
     num_loc = env.generator.num_loc if hasattr(env.generator, "num_loc") else 0xFFFFFFFF
     sel = torch.arange(num_starts, device=td.device).repeat_interleave(td.shape[0]) % num_loc
-    return sel if env.name == "tsp" else sel + 1
+    if env.name == "tsp":
+        return sel
+    sel = sel + 1
+    if env.name == "op" and (td["action_mask"][..., 1:].float().sum(-1) < num_starts).any():
+        # ops.py:150-160: some customers may be out of reach: resample the starts from the available ones
+        sel = torch.multinomial(td["action_mask"][..., 1:].float(), num_starts, replacement=True) + 1
+        sel = sel.t().reshape(-1)  # "b n -> (n b)"
+    return sel
 
 
 def get_tour_length_reward(locs, actions, with_depot: bool):

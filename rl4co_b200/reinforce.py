@@ -70,6 +70,9 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     kernel reported for the same actions.  `td` is the reset state (multistart: the [B] state,
     actions [S*B, T] in the reference's start-major order)."""
     env_name = env.name
+    if env_name not in ("tsp", "cvrp"):
+        raise NotImplementedError(f"the vectorised teacher-forced pass replays tsp / cvrp state only (got {env_name!r}); "
+                                  "use policy(td, env, actions=...) on the stepping kernels for evaluation")
     dec = policy.decoder
     if hidden is None:
         hidden, _ = policy.encoder(td)

@@ -62,7 +62,7 @@ def golden():
 
 
 def env_of(name):
-    return "tsp" if "tsp" in name else ("sdvrp" if "sdvrp" in name else "cvrp")
+    return "tsp" if "tsp" in name else ("sdvrp" if "sdvrp" in name else ("op" if "_op" in name else "cvrp"))
 
 
 def name_seeded_weights(state_dict, seed):

@@ -41,8 +41,16 @@ def make_env(name, n, check=True):
         import importlib
 
         Env = importlib.import_module("rl4co.envs.routing.sdvrp.env").SDVRPEnv
+    elif name == "op":
+        import importlib
+
+        Env = importlib.import_module("rl4co.envs.routing.op.env").OPEnv
     else:
         Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
+    if name == "op":
+        # the generator's default prize_distribution builds Uniform(1.0, 1.0), which current torch rejects at
+        # construction; "dist" skips that sampler (it is unused: the prizes come from prize_type, op/generator.py:115-125)
+        return Env(generator_params=dict(num_loc=n, prize_distribution="dist"), check_solution=check)
     return Env(generator_params=dict(num_loc=n), check_solution=check)
 
 
@@ -68,6 +76,9 @@ def env_fixture(name, n, batch, seed):
         if name == "sdvrp":
             visited.append(npy(td["demand_with_depot"]))  # the dynamic state of the split-delivery env
             used.append(npy(td["used_capacity"]))
+        if name == "op":
+            visited.append(npy(td["visited"]))
+            used.append(np.stack([npy(td["tour_length"]), npy(td["current_total_prize"])]))
     actions = torch.stack(actions, 1)
     reward = env.get_reward(td, actions)  # runs check_solution_validity too
     out.update(actions=npy(actions), action_mask=np.stack(masks), done=np.stack(dones),
@@ -76,20 +87,26 @@ def env_fixture(name, n, batch, seed):
         out.update(visited=np.stack(visited), used_capacity=np.stack(used))
     elif name == "sdvrp":
         out.update(demand_with_depot=np.stack(visited), used_capacity=np.stack(used))
+    elif name == "op":
+        st = np.stack(used)  # [T, 2, B]
+        out.update(visited=np.stack(visited), tour_length=st[:, 0], current_total_prize=st[:, 1])
     else:
         out.update(first_node=npy(td["first_node"]), i=npy(td["i"]))
     return out
 
 
-def sdvrp_am_fixture(n, batch, seed):
-    """SDVRP through the reference AttentionModelPolicy (VRPContext + SDVRPDynamicEmbedding, dynamic.py:60-78):
-    greedy, sampling with recorded noise, teacher-forced evaluation -- single-start decoding."""
+def sdvrp_am_fixture(n, batch, seed, name="sdvrp"):
+    """A sibling env through the reference AttentionModelPolicy -- SDVRP (VRPContext + SDVRPDynamicEmbedding,
+    dynamic.py:60-78) or OP (OPInitEmbedding init.py:254-280, OPContext context.py:201-213): greedy, sampling with
+    recorded noise, teacher-forced evaluation -- single-start decoding."""
     torch.manual_seed(seed)
-    env = make_env("sdvrp", n)
-    pol = ref.AttentionModelPolicy(env_name="sdvrp", num_encoder_layers=1).eval()
-    with torch.no_grad():  # the default init of a Linear(1, 3E) is small next to the static keys: make it count
-        pol.decoder.dynamic_embedding.projection.weight.mul_(3.0)
-    out = {"w::" + k: npy(v) for k, v in pol.state_dict().items() if k.startswith("decoder.")}
+    env = make_env(name, n)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=1).eval()
+    if name == "sdvrp":
+        with torch.no_grad():  # the default init of a Linear(1, 3E) is small next to the static keys: make it count
+            pol.decoder.dynamic_embedding.projection.weight.mul_(3.0)
+    keep = ("decoder.",) if name == "sdvrp" else ("decoder.", "encoder.")
+    out = {"w::" + k: npy(v) for k, v in pol.state_dict().items() if k.startswith(keep)}
     td0 = env.generator(batch_size=[batch])
     for k in td0.keys():
         out[f"inst::{k}"] = npy(td0[k])
@@ -355,6 +372,10 @@ def main():
         "env_sdvrp50": lambda: env_fixture("sdvrp", 50, 8, 105),
         "am_sdvrp20": lambda: sdvrp_am_fixture(20, 8, 206),
         "am_sdvrp50": lambda: sdvrp_am_fixture(50, 4, 207),
+        "env_op20": lambda: env_fixture("op", 20, 16, 108),
+        "env_op50": lambda: env_fixture("op", 50, 8, 109),
+        "am_op20": lambda: sdvrp_am_fixture(20, 8, 210, name="op"),
+        "am_op50": lambda: sdvrp_am_fixture(50, 4, 211, name="op"),
         "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
         "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
         "layout": layout_fixture,

@@ -7,9 +7,9 @@ import torch
 from oracle import am_rollout_oracle as O
 from conftest import env_of
 
-ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50", "env_sdvrp20", "env_sdvrp50"]
+ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50", "env_sdvrp20", "env_sdvrp50", "env_op20", "env_op50"]
 AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50", "am_tsp100", "am_cvrp100"]
-SD_FIX = ["am_sdvrp20", "am_sdvrp50"]  # sibling env (dynamic embedding), single-start decoding
+SD_FIX = ["am_sdvrp20", "am_sdvrp50", "am_op20", "am_op50"]  # sibling envs (sdvrp: dynamic embedding; op), single start
 
 
 @pytest.mark.parametrize("name", ENV_FIX)
@@ -30,12 +30,18 @@ def test_env_mdp_bit_exact(golden, name):
         if env == "sdvrp":
             assert torch.equal(st["demand_with_depot"], g["demand_with_depot"][t])
             assert torch.equal(st["used_capacity"], g["used_capacity"][t])
+        if env == "op":
+            assert torch.equal(st["visited"], g["visited"][t].bool())
+            assert torch.equal(st["tour_length"], g["tour_length"][t])
+            assert torch.equal(st["current_total_prize"], g["current_total_prize"][t])
     if env == "tsp":
         assert torch.equal(st["first_node"], g["first_node"])
         assert torch.equal(st["i"], g["i"])
         O.tsp_check_solution(actions)
     elif env == "sdvrp":
         O.sdvrp_check_solution(st, actions)
+    elif env == "op":
+        O.op_check_solution(st, actions)
     else:
         O.cvrp_check_solution(st, actions)
     r = O.env_reward(env, st, actions)
@@ -186,3 +192,12 @@ def test_pomo_config_c4_fixture(golden):
     max_r, max_aug = O.pomo_reduce(out["reward"], n_aug, N)[:2]
     torch.testing.assert_close(max_r, g["max_reward"])
     torch.testing.assert_close(max_aug, g["max_aug_reward"])
+
+
+@pytest.mark.parametrize("name", ["am_op20", "am_op50"])
+def test_op_encoder_from_instance(golden, name):
+    """OPInitEmbedding (init.py:254-280: depot / (x, y, prize)) + one encoder layer reproduce the recorded embeddings."""
+    g = golden(name)
+    st = O.env_reset("op", g.inst())
+    h, _ = O.encoder_forward(g.weights(), "op", st, num_layers=1, normalization="batch")
+    torch.testing.assert_close(h, g["h"], rtol=1e-5, atol=1e-5)
