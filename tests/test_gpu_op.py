@@ -139,6 +139,7 @@ def test_op_policy_vs_oracle_on_fresh_instances(n, batch):
     with torch.inference_mode():
         td = env.reset(td_host.to(DEV))
         out = pol(td, env, phase="test", decode_type="greedy")
+        td = env.reset(td_host.to(DEV))  # the stepping path advances the state in place, like the reference's loop
         ms = pol(td, env, phase="test", decode_type="multistart_greedy", num_starts=4)
     assert ms["reward"].shape[0] == 4 * batch and torch.isfinite(ms["log_likelihood"]).all()
     W = {k: v.detach().cpu() for k, v in pol.state_dict().items()}
