@@ -128,7 +128,8 @@ def test_op_policy_vs_golden(golden, name, mode, monkeypatch):
 @pytest.mark.parametrize("n,batch", [(20, 64), (100, 32)])
 def test_op_policy_vs_oracle_on_fresh_instances(n, batch):
     """Seeded fresh instances (on-device generator off: the CPU call order): teacher-forced oracle log-probs / rewards of
-    the GPU's own greedy actions, valid tours, and multistart decoding returns valid tours for every start."""
+    the GPU's own greedy and sampled actions, valid tours (check_solution=True); multistart decoding runs (its forced
+    starts ignore the budget exactly like ops.py:128-149, so their validity is not asserted)."""
     from rl4co_b200.envs import get_env
     from rl4co_b200.policy import FusedAttentionModelPolicy
 
@@ -140,11 +141,19 @@ def test_op_policy_vs_oracle_on_fresh_instances(n, batch):
         td = env.reset(td_host.to(DEV))
         out = pol(td, env, phase="test", decode_type="greedy")
         td = env.reset(td_host.to(DEV))  # the stepping path advances the state in place, like the reference's loop
-        ms = pol(td, env, phase="test", decode_type="multistart_greedy", num_starts=4)
+        smp = pol(td, env, phase="train", decode_type="sampling")
+        td = env.reset(td_host.to(DEV))
+        env_nc = get_env("op", generator_params=dict(num_loc=n), check_solution=False)
+        ms = pol(td, env_nc, phase="test", decode_type="multistart_greedy", num_starts=4)
     assert ms["reward"].shape[0] == 4 * batch and torch.isfinite(ms["log_likelihood"]).all()
+    assert (smp["reward"] >= 0).all() and (smp["actions"][:, -1] == 0).all()
     W = {k: v.detach().cpu() for k, v in pol.state_dict().items()}
     inst = {k: td_host[k] for k in td_host.keys()}
     with torch.inference_mode():
         ref = O.policy_forward(W, "op", inst, num_layers=2, actions=out["actions"].cpu(), faithful_copies=False)
     torch.testing.assert_close(out["reward"].cpu(), ref["reward"], rtol=RTOL, atol=1e-6)
     torch.testing.assert_close(out["log_likelihood"].cpu(), ref["log_likelihood"], rtol=RTOL, atol=ATOL_LP * 2)
+    with torch.inference_mode():
+        ref = O.policy_forward(W, "op", inst, num_layers=2, actions=smp["actions"].cpu(), faithful_copies=False)
+    torch.testing.assert_close(smp["reward"].cpu(), ref["reward"], rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(smp["log_likelihood"].cpu(), ref["log_likelihood"], rtol=RTOL, atol=ATOL_LP * 4)
