@@ -31,6 +31,13 @@ hi, lo = native.split_tf32(w)
 native.gemm_tf32x3(a, hi, lo, residual=torch.randn(300, 128, device=dev))
 torch.cuda.synchronize()
 print("gemm ok")
+# orienteering: stepping kernels only (co_op_step / co_op_action_mask / co_op_reward)
+env = get_env("op", generator_params=dict(num_loc=20), check_solution=True)
+pol = FusedAttentionModelPolicy(env_name="op", num_encoder_layers=1).to(dev).eval()
+with torch.inference_mode():
+    for dt in ("greedy", "sampling"):
+        out = pol(env.reset(env.generator(300).to(dev)), env, decode_type=dt)
+print("op ok", out["reward"].mean().item())
 # training-step attention kernels (forward, dQ, dK/dV) with a mask and strided key / value views; instance norm
 from rl4co_b200 import attention_train as AT
 
