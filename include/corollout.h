@@ -42,7 +42,8 @@ extern "C" {
 /* environment kinds (env.name in the reference: "tsp", "cvrp") */
 #define CO_ENV_TSP 0
 #define CO_ENV_CVRP 1
-#define CO_ENV_SDVRP 2 /* split-delivery VRP: VRP context + dynamic embedding; stepping kernels only */
+#define CO_ENV_SDVRP 2 /* split-delivery VRP: VRP context + dynamic embedding */
+#define CO_ENV_OP 3    /* orienteering: budget context, length mask, prize reward (co_rollout; the step kernels are co_op_*) */
 
 /* action-selection modes (rl4co/utils/decoding.py:426-461) */
 #define CO_SELECT_GREEDY 0       /* Greedy._step: argmax, first index on ties            */
@@ -224,6 +225,9 @@ typedef struct co_rollout_args {
   /* sdvrp: dynamic-embedding weights [wk | wv | W_out^T wl] = SDVRPDynamicEmbedding.projection.weight[:, 0] with
    * the logit third folded like block 2 of the cache (nn/env_embeddings/dynamic.py:60-78); NULL otherwise */
   const float* dyn_w;        /* [3E] */
+  /* op: per-node length budget max_length [B_inst, N] (op/env.py:121-123); `demand` carries the customers' prizes
+   * [B_inst, N-1], `vehicle_capacity` the budget at the depot max_length[:, 0], reward_out the collected prize */
+  const float* node_limit;
 } co_rollout_args;
 
 int co_cache_width(int env_kind); /* floats per node row of the widest rollout cache layout (tsp 5E, cvrp 4E) */

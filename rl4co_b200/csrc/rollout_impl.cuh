@@ -64,7 +64,8 @@ struct Smem {
   alignas(16) float zbuf[2][32 * SPL];  // masked, temperature-scaled logits of the last two steps (deferred log-prob)
   alignas(16) uint2 red[4];             // per selection warp: (best key as order-preserving uint, node)
   alignas(16) float lps[32];            // log-prob warp: lane partial sums of exp(z - Zb)
-  float dem[32 * SPL];
+  float dem[32 * SPL];                  // cvrp / sdvrp: demand; op: prize (node-indexed, depot 0)
+  float lim[32 * SPL];                  // op: max_length per node (budget minus the way back)
   float2 loc[32 * SPL];
   unsigned char order[32 * SPL];        // cvrp: customers sorted by demand (ascending)
   unsigned char rank_of[32 * SPL];      // cvrp: demand rank of each customer (inverse of `order`)
@@ -126,9 +127,18 @@ static __device__ __noinline__ void first_node_gemv(const float* __restrict__ w_
   if (half == 0) qfix[e] += sacc;
 }
 
+// 2-norm of a coordinate difference as torch's CPU reduction rounds it (op_kernels.cu): sqrt(fma(dy, dy, dx * dx))
+__device__ __forceinline__ float dist2_fma(float2 a, float2 b) {
+  const float dx = a.x - b.x, dy = a.y - b.y;
+  return sqrtf(fmaf(dy, dy, dx * dx));
+}
+
 template <int ENV>
 __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used, float thr, int cur, bool anyfeas) {
   if (ENV == CO_ENV_TSP) return !visbit;
+  // op/env.py:140-155: d = tour_length + dist(cur, n) (formed by the caller), thr = max_length[n], anyfeas = "the depot
+  // has been re-entered"; the depot itself is always feasible
+  if (ENV == CO_ENV_OP) return (n == 0) || (!visbit && !anyfeas && !(d > thr));
   // cvrp/env.py:126-136, sdvrp/env.py:110-116 (depot rule shared)
   if (n == 0) return !(cur == 0 && anyfeas);
   if (ENV == CO_ENV_SDVRP) return !visbit && !(d == 0.0f) && !(used >= thr);  // thr = capacity here; visbit = padding
@@ -144,6 +154,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
   constexpr bool first_table = (ENV == CO_ENV_TSP) && (CWB == 5);
   constexpr bool VRP = (ENV != CO_ENV_TSP);        // depot env with capacity context (cvrp, sdvrp)
   constexpr bool SD = (ENV == CO_ENV_SDVRP);       // split deliveries: dynamic demand + dynamic embedding
+  constexpr bool OP = (ENV == CO_ENV_OP);          // orienteering: `used` is the tour length, `cap` the budget at the depot
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<SPL>& sm = *reinterpret_cast<Smem<SPL>*>(smem_raw);
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     if (tid < NS) {
       sm.loc[tid] = (tid < N) ? reinterpret_cast<const float2*>(A.locs)[(size_t)b * N + tid] : make_float2(0.f, 0.f);
       sm.dem[tid] = (VRP && tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
+      if (OP) sm.lim[tid] = (tid < N) ? A.node_limit[(size_t)b * N + tid] : 0.f;
     }
     if (SD) {
       for (int i = tid; i < 3 * E; i += 256) sm.wdyn[i] = A.dyn_w[i];
@@ -239,10 +251,16 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       }
       __syncthreads();
     }
+    // per-thread node constants: (remaining) demand for cvrp / sdvrp; op: the node's length limit, plus its coordinates
     float dmk0[SPL];
+    float2 lck[SPL];
 #pragma unroll
-    for (int k = 0; k < SPL; ++k) dmk0[k] = sm.dem[nG + k];
-    const float dL0 = sm.dem[nL];
+    for (int k = 0; k < SPL; ++k) {
+      dmk0[k] = OP ? sm.lim[nG + k] : sm.dem[nG + k];
+      lck[k] = OP ? sm.loc[nG + k] : make_float2(0.f, 0.f);
+    }
+    const float dL0 = OP ? sm.lim[nL] : sm.dem[nL];
+    const float2 lcL = OP ? sm.loc[nL] : make_float2(0.f, 0.f);
     // scores split by linearity: q.K = ptab[cur].K + qfix.K + rem * (wcap.K); the last two are
     // per-episode / per-instance constants held in registers (FK, WK)
     auto head_dot = [&](const float* vec, float (&out)[SPL]) {
@@ -341,13 +359,19 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           mybits |= (dd < (unsigned)SPL) ? (1u << dd) : 0u;
           mybits |= (a == nL) ? 0x100u : 0u;
         }
-        if (h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
+        if (!OP && h == 0) {  // incremental tour length: warp 0 only (thread 0 writes the reward)
           const float2 pa = sm.loc[a], pp = sm.loc[prev];
           const float dx = pa.x - pp.x, dy = pa.y - pp.y;
           if (VRP || t != 0) dist += sqrtf(dx * dx + dy * dy);
         }
         if (ENV == CO_ENV_TSP) {
           if (t == 0) first = a;
+        } else if (OP) {
+          // op/env.py:72-105: the tour length feeds the mask and the context (every thread replays it, `used`); the
+          // collected prize is the reward (`dist`, warp 0); the depot re-entered after step 0 ends the episode
+          used = used + dist2_fma(sm.loc[a], sm.loc[prev]);
+          if (h == 0) dist += sm.dem[a];
+          depot_seen = depot_seen || (a == 0);
         } else if (SD) {
           // sdvrp/env.py:55-82: deliver min(remaining demand, remaining capacity); every thread replays the arithmetic.
           // sm.dem[a] is read by all threads here, so the owner's write-back waits until after the next block barrier.
@@ -384,7 +408,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         }
         prev = a; cur = a; ++t;
         // cvrp: all nodes incl. the depot visited; sdvrp: no positive demand left (sdvrp/env.py:71)
-        done = (ENV == CO_ENV_TSP) ? (t >= N) : (SD ? (nrem == 0) : (nvis >= N));
+        done = (ENV == CO_ENV_TSP) ? (t >= N) : (OP ? (a == 0 && t > 1) : (SD ? (nrem == 0) : (nvis >= N)));
       };
       // log-softmax(z)[a] of one finished step from its z row (log-prob warp; decoding.py:188,352-356): exact
       // exp-sum with the fixed offset Zb; masked nodes hold -inf -> 2^-inf = 0
@@ -467,9 +491,11 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           bool fz[SPL];
           // sdvrp: q_h . wk_h = ptab[cur]_h . wk_h + qfix_h . wk_h + rem * (wcap_h . wk_h)
           const float qwk = SD ? fmaf(rem, WKW, sm.pwk[cur * 8 + h] + FKW) : 0.f;
+          const float2 pcur = OP ? sm.loc[cur] : make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
-            fz[k] = feasible<ENV>(nG + k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
+            fz[k] = OP ? feasible<ENV>(nG + k, (mybits >> k) & 1u, used + dist2_fma(lck[k], pcur), used, dmk[k], cur, depot_seen)
+                       : feasible<ENV>(nG + k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
             float dot = (sc2[k].x + sc2[k].y) + FK[k];
             if (VRP) dot = fmaf(rem, WK[k], dot);
             if (SD) dot = fmaf(dmk[k], qwk, dot);  // q . (K[n] + d_n wk) = q.K[n] + d_n (q.wk)
@@ -549,7 +575,8 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
                                                                      // past the env_step that read the old value)
         if (sel_warp) {
           // ---------------- pointer logit of node nL: heads summed in fixed order, tanh clip, mask, temperature
-          const bool fzL = feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
+          const bool fzL = OP ? feasible<ENV>(nL, (mybits >> 8) & 1u, used + dist2_fma(lcL, sm.loc[cur]), used, dL, cur, depot_seen)
+                              : feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
           const float p = ((sm.part[0][nL] + sm.part[1][nL]) + (sm.part[2][nL] + sm.part[3][nL])) +
                           ((sm.part[4][nL] + sm.part[5][nL]) + (sm.part[6][nL] + sm.part[7][nL]));
           const float lg = tanhf(p * 0.08838834764831845f) * clip;  // /sqrt(E), tanh clip (decoding.py:169-170)
@@ -605,7 +632,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       if (tid == 0) {
         const float2 pa = sm.loc[(ENV == CO_ENV_TSP) ? first : 0], pp = sm.loc[prev];
         const float dx = pa.x - pp.x, dy = pa.y - pp.y;
-        A.reward_out[traj] = -(dist + sqrtf(dx * dx + dy * dy));
+        A.reward_out[traj] = OP ? dist : -(dist + sqrtf(dx * dx + dy * dy));  // op: the collected prize
         if (A.steps_out) A.steps_out[traj] = t;
         if (A.used_capacity_out) A.used_capacity_out[traj] = used;
         if (A.max_steps_out) atomicMax(A.max_steps_out, t);

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "gemm_tf32x3.cu",
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "rollout_op.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
            "ffn_fused.cu", "data_kernels.cu", "attn_train.cu", "norm_kernels.cu", "op_kernels.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
@@ -28,11 +28,10 @@ HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
 ENV_SDVRP = 2
-#: "op" shares the cvrp decoder arithmetic (context = [h_cur ; budget - spent], context.py:201-213): max_length[:, 0] and
-#: tour_length stand in for vehicle_capacity and used_capacity
-ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP, "op": ENV_CVRP}
+ENV_OP = 3
+ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP, "op": ENV_OP}
 #: environments the whole-episode kernel (co_rollout) is instantiated for; others take the stepping kernels
-ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp")
+ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp", "op")
 SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
 ROLLOUT_FORCED_START = 1
 EMBED_DIM, NUM_HEADS = 128, 8
@@ -66,7 +65,7 @@ class RolloutArgs(Structure):
         ("actions_out", c_void_p), ("logp_out", c_void_p), ("reward_out", c_void_p), ("loglik_out", c_void_p),
         ("steps_out", c_void_p), ("max_steps_out", c_void_p), ("used_capacity_out", c_void_p),
         ("node_emb", c_void_p), ("w_first", c_void_p), ("cache_width", c_int32), ("reserved0", c_int32),
-        ("dyn_w", c_void_p),
+        ("dyn_w", c_void_p), ("node_limit", c_void_p),
     ]
 
 
@@ -353,7 +352,9 @@ def pointer_logits(env_name, weights: DecoderWeights, node_emb, graph_ctx, K, V,
         if x.stride(2) != 1 or x.stride(1) != ld or x.stride(0) != N * ld:
             raise ValueError(f"{name}: unsupported strides {x.stride()}")
     logits = torch.empty(B_traj, N, dtype=F32, device=node_emb.device)
-    _check(lib().co_pointer_logits(ENV_KIND[env_name], ctypes.byref(weights), _ptr(node_emb, F32, "node_emb"),
+    # "op" shares the cvrp decoder arithmetic (context = [h_cur ; budget - spent], context.py:201-213): max_length[:, 0]
+    # and tour_length stand in for vehicle_capacity and used_capacity
+    _check(lib().co_pointer_logits(ENV_KIND["cvrp" if env_name == "op" else env_name], ctypes.byref(weights), _ptr(node_emb, F32, "node_emb"),
                                    _ptr(graph_ctx, F32, "graph_ctx"), _ptr(K, F32, "glimpse_key", True),
                                    _ptr(V, F32, "glimpse_val", True), _ptr(L, F32, "logit_key", True),
                                    _bool_ptr(mask, "action_mask"), _ptr(first_node, I64, "first_node"),
@@ -542,7 +543,8 @@ def reward_stats(reward, out2):
 @_on_device_of_first_tensor
 def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, locs, demand, vehicle_capacity,
             B_inst, N, num_starts=1, forced_start=False, num_loc=0, T_max=None, forced_actions=None, noise=None,
-            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0, node_emb=None, w_first=None, dyn_w=None):
+            tanh_clipping=10.0, temperature=1.0, seed=0, offset=0, node_emb=None, w_first=None, dyn_w=None,
+            node_limit=None):
     """Launch the persistent rollout kernel; returns dict of device tensors (no host sync).
     `cache` is [B_inst, N, W]: W = 4E ([K | V | L' | cur-table]; tsp then needs `node_emb` [B_inst, N, E] and
     `w_first` [E, E] for the per-episode first-node GEMV) or, tsp only, 5E (with the first-node table)."""
@@ -550,7 +552,7 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
     S = max(1, int(num_starts))
     B_traj = B_inst * S
     if T_max is None:
-        T_max = N if env_name == "tsp" else (2 * (N - 1) if env_name == "cvrp" else 3 * (N - 1) + 2)
+        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1}.get(env_name, 3 * (N - 1) + 2)
     actions = torch.empty(B_traj, T_max, dtype=I64, device=dev)
     logp = torch.empty(B_traj, T_max, dtype=F32, device=dev)
     reward = torch.empty(B_traj, dtype=F32, device=dev)
@@ -591,6 +593,10 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
         if dyn_w is None or tuple(dyn_w.shape) != (3 * EMBED_DIM,):
             raise ValueError("sdvrp needs dyn_w [3E] (dynamic-embedding weights, logit third folded)")
         a.dyn_w = _ptr(dyn_w, F32, "dyn_w")
+    if env_name == "op":
+        if node_limit is None or tuple(node_limit.shape) != (B_inst, N):
+            raise ValueError(f"op needs node_limit = max_length [{B_inst}, {N}]")
+        a.node_limit = _ptr(node_limit, F32, "node_limit")
     if forced_actions is not None and tuple(forced_actions.shape) != (B_traj, T_max):
         raise ValueError(f"forced_actions must be [{B_traj}, {T_max}], got {tuple(forced_actions.shape)}")
     if noise is not None and (noise.dim() != 3 or noise.shape[1] != B_traj or noise.shape[2] != N):

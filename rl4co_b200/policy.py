@@ -133,7 +133,7 @@ class FusedAttentionModelPolicy(nn.Module):
         B_traj = B * S
         # decode-step bound: tsp N; cvrp 2(N-1) (every customer + a depot return each); sdvrp 3(N-1)+2 (a customer can
         # be split once per refill on top of that)
-        T_max = N if env_name == "tsp" else (2 * (N - 1) if env_name == "cvrp" else 3 * (N - 1) + 2)
+        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1}.get(env_name, 3 * (N - 1) + 2)  # op: customers once + depot
         # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
         cached = self.decoder._precompute_cache(hidden, first_table=True if S > 1 else None)
 
@@ -163,7 +163,12 @@ class FusedAttentionModelPolicy(nn.Module):
         vrp = env_name in ("cvrp", "sdvrp")
         demand = td["demand"].contiguous() if vrp else None
         vcap = td["vehicle_capacity"].reshape(-1).contiguous() if vrp else None
-        num_loc = getattr(env.generator, "num_loc", N - (1 if vrp else 0))
+        node_limit = None
+        if env_name == "op":  # prizes ride in `demand`, the budget at the depot in `vehicle_capacity` (corollout.h)
+            demand = td["prize"][..., 1:].contiguous()
+            vcap = td["max_length"][..., 0].contiguous()
+            node_limit = td["max_length"].contiguous()
+        num_loc = getattr(env.generator, "num_loc", N - (1 if vrp or env_name == "op" else 0))
         with torch.no_grad():
             res = native.rollout(
                 env_name, mode, cached.rollout_cache.detach().contiguous(), cached.graph_context_or_none,
@@ -172,7 +177,8 @@ class FusedAttentionModelPolicy(nn.Module):
                 noise=noise.contiguous() if noise is not None else None, tanh_clipping=tanh_clipping,
                 temperature=temperature, seed=seed or 0, offset=philox_offset or 0,
                 node_emb=hidden.detach().contiguous() if env_name == "tsp" else None,
-                w_first=cached.w_first.detach() if cached.w_first is not None else None, dyn_w=cached.dyn_w)
+                w_first=cached.w_first.detach() if cached.w_first is not None else None, dyn_w=cached.dyn_w,
+                node_limit=node_limit)
         if env_name == "tsp":
             T = N
         elif decode_type == "evaluate":
@@ -193,8 +199,8 @@ class FusedAttentionModelPolicy(nn.Module):
                                                return_sum=False, temperature=temperature, tanh_clipping=tanh_clipping,
                                                forced_first=forced_start)
         if calc_reward and env.check_solution:
-            td_chk = td if S == 1 else TensorDict({k: td[k] for k in ("locs", "demand", "vehicle_capacity") if k in td.keys()},
-                                                  batch_size=td.batch_size)
+            td_chk = td if S == 1 else TensorDict({k: td[k] for k in ("locs", "demand", "vehicle_capacity", "max_length")
+                                                   if k in td.keys()}, batch_size=td.batch_size)
             self._check(env, td_chk, out_actions.contiguous(), S)
         if S > 1 and select_best:  # decoding.py:415-423
             _, max_idxs = unbatchify(reward, S).max(dim=-1)
@@ -208,6 +214,9 @@ class FusedAttentionModelPolicy(nn.Module):
 
     @staticmethod
     def _check(env, td, actions, S):
+        if env.name == "op":  # duplicates + length budget; rows of start-major trajectories share instances (j % B)
+            env.check_solution_validity(td, actions)
+            return
         if env.name == "tsp":
             bad = native.check_tours(actions, td["locs"].shape[-2])
         elif env.name == "sdvrp":  # torch replay on the device (validation path), start-major rows share instances

@@ -1,6 +1,7 @@
 """GPU: the second sibling env -- the orienteering problem (rl4co/envs/routing/op/env.py, OPInitEmbedding
-init.py:254-280, OPContext context.py:201-213) on the stepping kernels, against fixtures recorded from the unmodified
-reference (`env_op*.npz`, `am_op*.npz`) and against the CPU oracle."""
+init.py:254-280, OPContext context.py:201-213) on the stepping kernels and inside the persistent kernel (ENV = op behind
+the mask functor: length-budget mask, prize sum as reward), against fixtures recorded from the unmodified reference
+(`env_op*.npz`, `am_op*.npz`) and against the CPU oracle."""
 
 import pytest
 import torch
@@ -90,7 +91,8 @@ def test_op_decoder_step_vs_reference_logits(golden, name):
 
 @pytest.mark.parametrize("name", ["am_op20", "am_op50"])
 @pytest.mark.parametrize("mode", ["greedy", "sampling", "evaluate"])
-def test_op_policy_vs_golden(golden, name, mode, monkeypatch):
+@pytest.mark.parametrize("fused", [True, False])
+def test_op_policy_vs_golden(golden, name, mode, fused, monkeypatch):
     from rl4co_b200 import decoding
     from rl4co_b200.envs import get_env
     from rl4co_b200.tensordict import TensorDict
@@ -101,7 +103,13 @@ def test_op_policy_vs_golden(golden, name, mode, monkeypatch):
     B = inst["locs"].shape[0]
     env = get_env("op", generator_params=dict(num_loc=inst["locs"].shape[1]), check_solution=True)
     td = env.reset(TensorDict(inst, batch_size=[B]))
-    if mode == "sampling":  # serve the Exp(1) draws torch.multinomial consumed, one per step
+    N = inst["locs"].shape[1] + 1
+    if mode == "sampling" and fused:  # recorded-noise protocol, padded to the kernel's step bound
+        q = g["sampling_noise"]
+        qpad = torch.ones(N + 1, q.shape[1], q.shape[2])
+        qpad[: q.shape[0]] = q
+        kw = dict(decode_type="sampling", noise=qpad.to(DEV))
+    elif mode == "sampling":  # stepping path: serve the Exp(1) draws torch.multinomial consumed, one per step
         served = iter(g["sampling_noise"].to(DEV).unbind(0))
         monkeypatch.setattr(decoding.Sampling, "_noise", lambda self, logits: next(served).contiguous())
         kw = dict(decode_type="sampling")
@@ -110,7 +118,7 @@ def test_op_policy_vs_golden(golden, name, mode, monkeypatch):
     else:
         kw = dict(decode_type="greedy")
     with torch.inference_mode():
-        out = pol(td, env, phase="test", return_sum_log_likelihood=False, **kw)
+        out = pol(td, env, phase="test", return_sum_log_likelihood=False, fused_rollout=fused, **kw)
     key = {"greedy": "greedy", "sampling": "sampling", "evaluate": "eval"}[mode]
     ra, rl, rr = g[f"{key}_actions"], g[f"{key}_logprobs"], g[f"{key}_reward"]
     if mode == "evaluate":
@@ -157,3 +165,25 @@ def test_op_policy_vs_oracle_on_fresh_instances(n, batch):
         ref = O.policy_forward(W, "op", inst, num_layers=2, actions=smp["actions"].cpu(), faithful_copies=False)
     torch.testing.assert_close(smp["reward"].cpu(), ref["reward"], rtol=RTOL, atol=1e-6)
     torch.testing.assert_close(smp["log_likelihood"].cpu(), ref["log_likelihood"], rtol=RTOL, atol=ATOL_LP * 4)
+
+
+def test_op_fused_equals_stepping():
+    """Persistent kernel == stepping kernels on the same instances (sampling with one shared noise tensor, so the
+    trajectories are long), with check_solution=True validating every tour."""
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+
+    torch.manual_seed(5)
+    n, B = 50, 256
+    env = get_env("op", generator_params=dict(num_loc=n), check_solution=True)
+    pol = FusedAttentionModelPolicy(env_name="op", num_encoder_layers=1).to(DEV).eval()
+    pol.decoder.cache_gemm = "cublas"
+    td_host = env.generator(B)
+    with torch.inference_mode():
+        a = pol(env.reset(td_host.to(DEV)), env, phase="test", decode_type="sampling", seed=3, return_sum_log_likelihood=False)
+        b = pol(env.reset(td_host.to(DEV)), env, phase="test", actions=a["actions"], fused_rollout=False,
+                return_sum_log_likelihood=False)
+    assert (a["actions"][:, -1] == 0).all() and (a["actions"] != 0).any(1).float().mean() > 0.5
+    T = min(a["log_likelihood"].shape[1], b["log_likelihood"].shape[1])
+    torch.testing.assert_close(a["log_likelihood"][:, :T], b["log_likelihood"][:, :T], rtol=RTOL, atol=ATOL_LP)
+    torch.testing.assert_close(a["reward"], b["reward"], rtol=RTOL, atol=1e-6)
