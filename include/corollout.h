@@ -44,6 +44,7 @@ extern "C" {
 #define CO_ENV_CVRP 1
 #define CO_ENV_SDVRP 2 /* split-delivery VRP: VRP context + dynamic embedding */
 #define CO_ENV_OP 3    /* orienteering: budget context, length mask, prize reward (co_rollout; the step kernels are co_op_*) */
+#define CO_ENV_PCTSP 4 /* prize-collecting TSP: remaining-prize context, depot rule on the collected prize (co_pctsp_*) */
 
 /* action-selection modes (rl4co/utils/decoding.py:426-461) */
 #define CO_SELECT_GREEDY 0       /* Greedy._step: argmax, first index on ties            */
@@ -107,6 +108,15 @@ int co_op_step(const int64_t* action, const float* locs, const float* prize, con
                const uint8_t* visited_in, uint8_t* visited_out, float* tour_length, float* current_total_prize,
                int64_t* current_node, int64_t* i, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream);
 int co_op_reward(const float* prize, const int64_t* actions, float* reward, int B, int N, int T, void* stream);
+
+/* PCTSPEnv (rl4co/envs/routing/pctsp/env.py; sibling env, prize-collecting TSP): real_prize / penalty [B,N] (depot 0),
+ * visited [B,N] bool, cur_total_prize / cur_total_penalty [B] f32, current_node / i [B] i64 (in place).
+ * co_pctsp_step = _step :62-93 + get_action_mask :143-151; the reward (:153-172) is co_op_reward over the penalties plus
+ * co_tour_length. */
+int co_pctsp_action_mask(const uint8_t* visited, const float* cur_total_prize, uint8_t* mask_out, int B, int N, void* stream);
+int co_pctsp_step(const int64_t* action, const float* real_prize, const float* penalty, const uint8_t* visited_in,
+                  uint8_t* visited_out, float* cur_total_prize, float* cur_total_penalty, int64_t* current_node, int64_t* i,
+                  uint8_t* done, uint8_t* mask_out, int B, int N, void* stream);
 
 int co_tour_length(const float* locs, const int64_t* actions, float* reward, int B,
                    int B_locs, int N, int T, int with_depot, void* stream);
@@ -226,7 +236,8 @@ typedef struct co_rollout_args {
    * the logit third folded like block 2 of the cache (nn/env_embeddings/dynamic.py:60-78); NULL otherwise */
   const float* dyn_w;        /* [3E] */
   /* op: per-node length budget max_length [B_inst, N] (op/env.py:121-123); `demand` carries the customers' prizes
-   * [B_inst, N-1], `vehicle_capacity` the budget at the depot max_length[:, 0], reward_out the collected prize */
+   * [B_inst, N-1], `vehicle_capacity` the budget at the depot max_length[:, 0], reward_out the collected prize;
+   * pctsp: penalty per node [B_inst, N] (depot 0); `demand` = real prizes [B_inst, N-1], `vehicle_capacity` = prize_required */
   const float* node_limit;
 } co_rollout_args;
 

@@ -359,8 +359,73 @@ def op_check_solution(st, actions, add_distance_to_depot: bool = True):
     assert (length[..., None] <= max_length + 1e-5).all(), "Max length exceeded"
 
 
-ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset, "sdvrp": sdvrp_reset, "op": op_reset}
-ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step, "sdvrp": sdvrp_step, "op": op_step}
+# reference: rl4co/envs/routing/pctsp/env.py (prize-collecting TSP: collect prize >= 1, pay the penalties of the rest)
+
+
+def pctsp_action_mask(st):
+    """pctsp/env.py:143-151: customers: visited or the depot re-entered; depot: infeasible while the collected prize is
+    below 1.0 (a literal, not prize_required) and unvisited customers remain"""
+    mask = st["visited"] | st["visited"][..., 0:1]
+    mask[..., 0] = (st["cur_total_prize"] < 1.0) & (st["visited"][..., 1:].int().sum(-1) < st["visited"][..., 1:].size(-1))
+    return ~(mask > 0)
+
+
+def pctsp_reset(depot, locs, deterministic_prize, penalty, prize_required: float = 1.0):
+    """pctsp/env.py:95-141 (deterministic prizes: real_prize = expected_prize)"""
+    B = locs.shape[0]
+    dev = locs.device
+    st = {
+        "locs": torch.cat([depot[..., None, :], locs], dim=-2),
+        "current_node": torch.zeros((B,), dtype=torch.int64, device=dev),
+        "expected_prize": deterministic_prize,
+        "real_prize": torch.cat([torch.zeros_like(deterministic_prize[..., :1]), deterministic_prize], dim=-1),
+        "penalty": F.pad(penalty, (1, 0), mode="constant", value=0),
+        "cur_total_prize": torch.zeros(B, device=dev),
+        "cur_total_penalty": penalty.sum(-1),
+        "visited": torch.zeros((B, locs.shape[-2] + 1), dtype=torch.bool, device=dev),
+        "prize_required": torch.full((B,), prize_required, device=dev),
+        "i": torch.zeros((B,), dtype=torch.int64, device=dev),
+    }
+    st["action_mask"] = pctsp_action_mask(st)
+    st["done"] = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+    return st
+
+
+def pctsp_step(state, action):
+    """pctsp/env.py:62-93"""
+    st = dict(state)
+    cur_total_prize = st["cur_total_prize"] + gather_by_index(st["real_prize"], action)
+    cur_total_penalty = st["cur_total_penalty"] + gather_by_index(st["penalty"], action)
+    visited = st["visited"].scatter(-1, action[..., None], 1)
+    done = (st["i"] > 0) & (action == 0)
+    st.update(current_node=action, cur_total_prize=cur_total_prize, cur_total_penalty=cur_total_penalty, visited=visited,
+              i=st["i"] + 1, reward=torch.zeros_like(done), done=done, action=action)
+    st["action_mask"] = pctsp_action_mask(st)
+    return st
+
+
+def pctsp_reward(st, actions):
+    """pctsp/env.py:153-172: saved penalties - (tour length from / to the depot + all penalties)"""
+    if actions.size(-1) == 1:
+        assert (actions == 0).all(), "If all length 1 tours, they should be zero"
+        return torch.zeros(actions.size(0), dtype=torch.float, device=actions.device)
+    locs_ordered = torch.cat([st["locs"][..., 0:1, :], gather_by_index(st["locs"], actions)], dim=1)
+    length = get_tour_length(locs_ordered)
+    saved_penalty = st["penalty"].gather(1, actions)
+    return saved_penalty.sum(-1) - (length + st["penalty"][..., 1:].sum(-1))
+
+
+def pctsp_check_solution(st, actions):
+    """pctsp/env.py:174-197"""
+    sorted_actions = actions.sort(1)[0]
+    assert ((sorted_actions[..., 1:] == 0) | (sorted_actions[..., 1:] > sorted_actions[..., :-1])).all(), "Duplicates"
+    p = st["real_prize"].gather(1, actions)
+    assert ((p.sum(-1) >= 1 - 1e-5) | (sorted_actions.size(-1) - (sorted_actions == 0).int().sum(-1)
+                                       == (st["locs"].size(-2) - 1))).all(), "Total prize does not satisfy min total prize"
+
+
+ENV_RESET = {"tsp": tsp_reset, "cvrp": cvrp_reset, "sdvrp": sdvrp_reset, "op": op_reset, "pctsp": pctsp_reset}
+ENV_STEP = {"tsp": tsp_step, "cvrp": cvrp_step, "sdvrp": sdvrp_step, "op": op_step, "pctsp": pctsp_step}
 
 
 def env_reset(env_name, inst):
@@ -371,12 +436,16 @@ def env_reset(env_name, inst):
         return sdvrp_reset(inst["depot"], inst["locs"], inst["demand"])
     if env_name == "op":
         return op_reset(inst["depot"], inst["locs"], inst["prize"], inst["max_length"])
+    if env_name == "pctsp":
+        return pctsp_reset(inst["depot"], inst["locs"], inst["deterministic_prize"], inst["penalty"])
     return cvrp_reset(inst["depot"], inst["locs"], inst["demand"])
 
 
 def env_reward(env_name, st, actions):
     if env_name == "op":
         return op_reward(st, actions)
+    if env_name == "pctsp":
+        return pctsp_reward(st, actions)
     return tsp_reward(st["locs"], actions) if env_name == "tsp" else cvrp_reward(st["locs"], actions)
 
 
@@ -402,6 +471,14 @@ def generate_instances(env_name, batch, num_loc, generator=None):
         prize = (1 + (prize / prize.max(dim=-1, keepdim=True)[0] * 99).int()).float() / 100
         ml = OP_MAX_LENGTHS.get(num_loc) or OP_MAX_LENGTHS[min(OP_MAX_LENGTHS, key=lambda x: abs(x - num_loc))]
         return {"locs": locs[:, 1:, :], "depot": locs[:, 0, :], "prize": prize, "max_length": torch.full((batch,), ml)}
+    if env_name == "pctsp":  # pctsp/generator.py:36-139: penalty, deterministic prize, stochastic prize, in that order
+        locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
+        mp = OP_MAX_LENGTHS.get(num_loc) or OP_MAX_LENGTHS[min(OP_MAX_LENGTHS, key=lambda x: abs(x - num_loc))]
+        penalty = uni((batch, num_loc), 0.0, mp * 3.0 / num_loc)
+        det = uni((batch, num_loc), 0.0, 4.0 / num_loc)
+        sto = uni((batch, num_loc), 0.0, 2.0) * det
+        return {"locs": locs[:, 1:, :], "depot": locs[:, 0, :], "penalty": penalty, "deterministic_prize": det,
+                "stochastic_prize": sto}
     # cvrp and sdvrp share CVRPGenerator (sdvrp/env.py:47-54)
     locs = uni((batch, num_loc + 1, 2), 0.0, 1.0)
     demand = uni((batch, num_loc), 0.0, 9.0)
@@ -455,6 +532,13 @@ def op_context(weights, emb, st):
     return F.linear(torch.cat([cur, state_emb], -1), _w(weights, "context_embedding.project_context.weight"))
 
 
+def pctsp_context(weights, emb, st):
+    """nn/env_embeddings/context.py:61-74,184-198 (PCTSPContext): [h_cur ; clamp(prize_required - cur_total_prize, 0)]"""
+    cur = gather_by_index(emb, st["current_node"])
+    state_emb = torch.clamp(st["prize_required"] - st["cur_total_prize"], min=0)[..., None]
+    return F.linear(torch.cat([cur, state_emb], -1), _w(weights, "context_embedding.project_context.weight"))
+
+
 def pointer_logits(weights, q, K, V, L, mask, num_heads=8):
     """nn/attention.py:274-320 (PointerAttention.forward, mask_inner=True, no out bias)"""
     def heads(x):  # "... g (h s) -> ... h g s"
@@ -479,7 +563,8 @@ def decoder_forward(weights, env_name, st, cache, num_starts=0, faithful_copies=
     if two_batch_dims and isinstance(g, torch.Tensor):
         g = g.unsqueeze(1)
     ctx = (tsp_context(weights, emb, st) if env_name == "tsp" else
-           op_context(weights, emb, st) if env_name == "op" else vrp_context(weights, emb, st))  # cvrp, sdvrp
+           op_context(weights, emb, st) if env_name == "op" else
+           pctsp_context(weights, emb, st) if env_name == "pctsp" else vrp_context(weights, emb, st))  # cvrp, sdvrp
     q = ctx + g
     q = q.unsqueeze(1) if q.ndim == 2 else q
     K, V, L = cache["glimpse_key"], cache["glimpse_val"], cache["logit_key"]
@@ -713,7 +798,11 @@ def init_embedding(weights, env_name, st):
         return F.linear(st["locs"], weights[p + "init_embed.weight"], weights[p + "init_embed.bias"])
     depot, cities = st["locs"][:, :1, :], st["locs"][:, 1:, :]
     de = F.linear(depot, weights[p + "init_embed_depot.weight"], weights[p + "init_embed_depot.bias"])
-    feat = st["prize"][..., 1:, None] if env_name == "op" else st["demand"][..., None]  # init.py:254-280 / 115-136
+    feat = st["prize"][..., 1:, None] if env_name == "op" else None  # init.py:254-280 / 115-136
+    if env_name == "pctsp":  # init.py:221-251: (x, y, expected prize, penalty)
+        feat = torch.stack((st["expected_prize"], st["penalty"][..., 1:]), -1)
+    elif feat is None:
+        feat = st["demand"][..., None]
     ne = F.linear(torch.cat((cities, feat), -1), weights[p + "init_embed.weight"], weights[p + "init_embed.bias"])
     return torch.cat((de, ne), -2)
 

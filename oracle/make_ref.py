@@ -50,6 +50,9 @@ FILES = [
     "rl4co/envs/routing/op/env.py",
     "rl4co/envs/routing/op/generator.py",
     "rl4co/envs/routing/op/render.py",
+    "rl4co/envs/routing/pctsp/env.py",
+    "rl4co/envs/routing/pctsp/generator.py",
+    "rl4co/envs/routing/pctsp/render.py",
     "rl4co/models/common/constructive/__init__.py",
     "rl4co/models/common/constructive/base.py",
     "rl4co/models/common/constructive/autoregressive/__init__.py",

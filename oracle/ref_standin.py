@@ -184,6 +184,7 @@ def install() -> None:
     _pkg("rl4co.envs.routing.cvrp", "rl4co/envs/routing/cvrp")
     _pkg("rl4co.envs.routing.sdvrp", "rl4co/envs/routing/sdvrp")
     _pkg("rl4co.envs.routing.op", "rl4co/envs/routing/op")
+    _pkg("rl4co.envs.routing.pctsp", "rl4co/envs/routing/pctsp")
     _pkg("rl4co.models", "rl4co/models")
     _pkg("rl4co.models.common", "rl4co/models/common")
     _pkg("rl4co.models.nn", "rl4co/models/nn")

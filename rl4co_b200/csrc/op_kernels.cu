@@ -114,3 +114,80 @@ extern "C" int co_op_reward(const float* prize, const int64_t* actions, float* r
   op_reward_kernel<<<(B + OP_ROWS_PER_CTA - 1) / OP_ROWS_PER_CTA, 256, 0, (cudaStream_t)stream>>>(prize, actions, reward, B, N, T);
   return check_launch("co_op_reward");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Prize-collecting TSP (third sibling env): rl4co/envs/routing/pctsp/env.py
+//   co_pctsp_step        <- _step :62-93 + get_action_mask :143-151
+//   co_pctsp_action_mask <- get_action_mask: customers masked once visited or once the depot was re-entered; the depot is
+//                           infeasible while the collected prize is below 1.0 and unvisited customers remain
+// (reward = co_op_reward over the penalties + co_tour_length, see FusedPCTSPEnv._get_reward)
+namespace co {
+
+__device__ __forceinline__ void pctsp_mask_row(const uint8_t* visited, float prize, uint8_t* mask_out, int N, int lane) {
+  const bool depot_seen = visited[0] != 0;
+  int unvisited = 0;
+  for (int n = 1 + lane; n < N; n += 32) {
+    const bool v = visited[n] != 0;
+    mask_out[n] = (v || depot_seen) ? 0 : 1;
+    unvisited += v ? 0 : 1;
+  }
+  unvisited = __reduce_add_sync(FULL, unvisited);
+  if (lane == 0) mask_out[0] = ((prize < 1.0f) && (unvisited > 0)) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) pctsp_mask_kernel(const uint8_t* __restrict__ visited, const float* __restrict__ prize,
+                                                         uint8_t* mask_out, int B, int N) {
+  const int row = blockIdx.x * OP_ROWS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  pctsp_mask_row(visited + (size_t)row * N, prize[row], mask_out + (size_t)row * N, N, lane);
+}
+
+__global__ void __launch_bounds__(256) pctsp_step_kernel(const int64_t* __restrict__ action, const float* __restrict__ real_prize,
+                                                         const float* __restrict__ penalty, const uint8_t* visited_in,
+                                                         uint8_t* visited_out, float* total_prize, float* total_penalty,
+                                                         int64_t* current_node, int64_t* i, uint8_t* done, uint8_t* mask_out,
+                                                         int B, int N) {
+  const int row = blockIdx.x * OP_ROWS_PER_CTA + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int a = (int)action[row];
+  const float p = total_prize[row] + real_prize[(size_t)row * N + a];
+  const uint8_t* vin = visited_in + (size_t)row * N;
+  uint8_t* vout = visited_out + (size_t)row * N;
+  for (int n = lane; n < N; n += 32) vout[n] = (n == a) ? 1 : vin[n];
+  __syncwarp();
+  pctsp_mask_row(vout, p, mask_out + (size_t)row * N, N, lane);
+  if (lane == 0) {
+    const int64_t iv = i[row];
+    total_prize[row] = p;
+    total_penalty[row] += penalty[(size_t)row * N + a];
+    done[row] = (iv > 0) && (a == 0);
+    current_node[row] = a;
+    i[row] = iv + 1;
+  }
+}
+
+}  // namespace co
+
+extern "C" int co_pctsp_action_mask(const uint8_t* visited, const float* cur_total_prize, uint8_t* mask_out, int B, int N,
+                                    void* stream) {
+  if (!visited || !cur_total_prize || !mask_out) return fail(CO_ERR_BAD_ARG, "co_pctsp_action_mask: null pointer%s");
+  if (B < 0 || N < 2) return fail(CO_ERR_BAD_ARG, "co_pctsp_action_mask: bad shape%s B=%lld N=%lld", "", B, N);
+  if (B == 0) return CO_OK;
+  pctsp_mask_kernel<<<(B + OP_ROWS_PER_CTA - 1) / OP_ROWS_PER_CTA, 256, 0, (cudaStream_t)stream>>>(visited, cur_total_prize,
+                                                                                                   mask_out, B, N);
+  return check_launch("co_pctsp_action_mask");
+}
+
+extern "C" int co_pctsp_step(const int64_t* action, const float* real_prize, const float* penalty, const uint8_t* visited_in,
+                             uint8_t* visited_out, float* cur_total_prize, float* cur_total_penalty, int64_t* current_node,
+                             int64_t* i, uint8_t* done, uint8_t* mask_out, int B, int N, void* stream) {
+  if (!action || !real_prize || !penalty || !visited_in || !visited_out || !cur_total_prize || !cur_total_penalty ||
+      !current_node || !i || !done || !mask_out)
+    return fail(CO_ERR_BAD_ARG, "co_pctsp_step: null pointer%s");
+  if (B < 0 || N < 2) return fail(CO_ERR_BAD_ARG, "co_pctsp_step: bad shape%s B=%lld N=%lld", "", B, N);
+  if (B == 0) return CO_OK;
+  pctsp_step_kernel<<<(B + OP_ROWS_PER_CTA - 1) / OP_ROWS_PER_CTA, 256, 0, (cudaStream_t)stream>>>(
+      action, real_prize, penalty, visited_in, visited_out, cur_total_prize, cur_total_penalty, current_node, i, done, mask_out,
+      B, N);
+  return check_launch("co_pctsp_step");
+}

@@ -9,6 +9,7 @@ int rollout_tsp(const co_rollout_args& A, cudaStream_t st);
 int rollout_cvrp(const co_rollout_args& A, cudaStream_t st);
 int rollout_sdvrp(const co_rollout_args& A, cudaStream_t st);
 int rollout_op(const co_rollout_args& A, cudaStream_t st);
+int rollout_pctsp(const co_rollout_args& A, cudaStream_t st);
 int rollout_ms_tsp(const co_rollout_args& A, cudaStream_t st);   // query-batched (num_starts > 1)
 int rollout_ms_cvrp(const co_rollout_args& A, cudaStream_t st);
 }  // namespace co
@@ -17,7 +18,7 @@ using namespace co;
 
 extern "C" int co_cache_width(int env_kind) {
   return env_kind == CO_ENV_TSP ? 5 * E
-                                : ((env_kind == CO_ENV_CVRP || env_kind == CO_ENV_SDVRP || env_kind == CO_ENV_OP) ? 4 * E : 0);
+                                : ((env_kind == CO_ENV_CVRP || env_kind == CO_ENV_SDVRP || env_kind == CO_ENV_OP || env_kind == CO_ENV_PCTSP) ? 4 * E : 0);
 }
 extern "C" int co_rollout_max_nodes(void) { return 128; }
 
@@ -64,6 +65,12 @@ extern "C" int co_rollout(const co_rollout_args* args, void* stream) {
       return fail(CO_ERR_BAD_ARG, "co_rollout: demand / w_capacity / dyn_w required for sdvrp%s");
     if (A.cache_width != 4 * E) return fail(CO_ERR_BAD_ARG, "co_rollout: sdvrp cache_width must be 4E%s");
     return rollout_sdvrp(A, st);
+  }
+  if (A.env_kind == CO_ENV_PCTSP) {  // demand = real prizes [B, N-1], vehicle_capacity = prize_required, node_limit = penalties
+    if (!A.demand || !A.w_capacity || !A.vehicle_capacity || !A.node_limit)
+      return fail(CO_ERR_BAD_ARG, "co_rollout: prize (demand) / w_capacity / prize_required (vehicle_capacity) / penalty (node_limit) required for pctsp%s");
+    if (A.cache_width != 4 * E) return fail(CO_ERR_BAD_ARG, "co_rollout: pctsp cache_width must be 4E%s");
+    return rollout_pctsp(A, st);
   }
   if (A.env_kind == CO_ENV_OP) {  // single-trajectory kernel only (S > 1 loops over the trajectories inside it)
     if (!A.demand || !A.w_capacity || !A.vehicle_capacity || !A.node_limit)

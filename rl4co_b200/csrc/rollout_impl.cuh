@@ -65,7 +65,7 @@ struct Smem {
   alignas(16) uint2 red[4];             // per selection warp: (best key as order-preserving uint, node)
   alignas(16) float lps[32];            // log-prob warp: lane partial sums of exp(z - Zb)
   float dem[32 * SPL];                  // cvrp / sdvrp: demand; op: prize (node-indexed, depot 0)
-  float lim[32 * SPL];                  // op: max_length per node (budget minus the way back)
+  float lim[32 * SPL];                  // op: max_length per node (budget minus the way back); pctsp: penalty per node
   float2 loc[32 * SPL];
   unsigned char order[32 * SPL];        // cvrp: customers sorted by demand (ascending)
   unsigned char rank_of[32 * SPL];      // cvrp: demand rank of each customer (inverse of `order`)
@@ -139,6 +139,8 @@ __device__ __forceinline__ bool feasible(int n, bool visbit, float d, float used
   // op/env.py:140-155: d = tour_length + dist(cur, n) (formed by the caller), thr = max_length[n], anyfeas = "the depot
   // has been re-entered"; the depot itself is always feasible
   if (ENV == CO_ENV_OP) return (n == 0) || (!visbit && !anyfeas && !(d > thr));
+  // pctsp/env.py:143-151: d != 0 = "the depot has been re-entered", anyfeas = "unvisited customers remain", used = prize
+  if (ENV == CO_ENV_PCTSP) return (n == 0) ? !((used < 1.0f) && anyfeas) : (!visbit && d == 0.0f);
   // cvrp/env.py:126-136, sdvrp/env.py:110-116 (depot rule shared)
   if (n == 0) return !(cur == 0 && anyfeas);
   if (ENV == CO_ENV_SDVRP) return !visbit && !(d == 0.0f) && !(used >= thr);  // thr = capacity here; visbit = padding
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
   constexpr bool VRP = (ENV != CO_ENV_TSP);        // depot env with capacity context (cvrp, sdvrp)
   constexpr bool SD = (ENV == CO_ENV_SDVRP);       // split deliveries: dynamic demand + dynamic embedding
   constexpr bool OP = (ENV == CO_ENV_OP);          // orienteering: `used` is the tour length, `cap` the budget at the depot
+  constexpr bool PC = (ENV == CO_ENV_PCTSP);       // prize collecting: `used` is the collected prize, `cap` prize_required
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<SPL>& sm = *reinterpret_cast<Smem<SPL>*>(smem_raw);
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
     if (tid < NS) {
       sm.loc[tid] = (tid < N) ? reinterpret_cast<const float2*>(A.locs)[(size_t)b * N + tid] : make_float2(0.f, 0.f);
       sm.dem[tid] = (VRP && tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
-      if (OP) sm.lim[tid] = (tid < N) ? A.node_limit[(size_t)b * N + tid] : 0.f;
+      if (OP || PC) sm.lim[tid] = (tid < N) ? A.node_limit[(size_t)b * N + tid] : 0.f;  // op: length limit; pctsp: penalty
     }
     if (SD) {
       for (int i = tid; i < 3 * E; i += 256) sm.wdyn[i] = A.dyn_w[i];
@@ -342,6 +345,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       int pend_a = -1;              // sdvrp: demand write-back deferred past the next barrier (see env_step)
       float pend_d = 0.f, FKW = 0.f;
       float ll = 0.f;               // log-likelihood, accumulated by lane 0 of the log-prob warp
+      float pen = 0.f;              // pctsp: penalties of the visited customers (warp 0)
       // sdvrp serves demand in place (sm.dem): every further trajectory of the instance starts from the original demands
       // (every thread is past the previous trajectory's last read: the epilogue barrier)
       if (SD && s > 0 && tid < NS) sm.dem[tid] = (tid >= 1 && tid < N) ? A.demand[(size_t)b * (N - 1) + tid - 1] : 0.f;
@@ -371,6 +375,12 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
           // collected prize is the reward (`dist`, warp 0); the depot re-entered after step 0 ends the episode
           used = used + dist2_fma(sm.loc[a], sm.loc[prev]);
           if (h == 0) dist += sm.dem[a];
+          depot_seen = depot_seen || (a == 0);
+        } else if (PC) {
+          // pctsp/env.py:62-93: collected prize (replicated: depot rule + context), saved penalties (warp 0, reward)
+          used = used + sm.dem[a];
+          if (h == 0) pen += sm.lim[a];
+          nvis += (a != 0) ? 1 : 0;
           depot_seen = depot_seen || (a == 0);
         } else if (SD) {
           // sdvrp/env.py:55-82: deliver min(remaining demand, remaining capacity); every thread replays the arithmetic.
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         }
         prev = a; cur = a; ++t;
         // cvrp: all nodes incl. the depot visited; sdvrp: no positive demand left (sdvrp/env.py:71)
-        done = (ENV == CO_ENV_TSP) ? (t >= N) : (OP ? (a == 0 && t > 1) : (SD ? (nrem == 0) : (nvis >= N)));
+        done = (ENV == CO_ENV_TSP) ? (t >= N) : ((OP || PC) ? (a == 0 && t > 1) : (SD ? (nrem == 0) : (nvis >= N)));
       };
       // log-softmax(z)[a] of one finished step from its z row (log-prob warp; decoding.py:188,352-356): exact
       // exp-sum with the fixed offset Zb; masked nodes hold -inf -> 2^-inf = 0
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         // ---------------- glimpse + this head's share of every pointer logit: warp h = head h, fully warp-local
         {
           const float4* pr = reinterpret_cast<const float4*>(sm.ptab + cur * E + h * D);
-          const float rem = cap - used;  // context.py:147-149
+          const float rem = PC ? fmaxf(cap - used, 0.0f) : cap - used;  // context.py:147-149; pctsp :184-198 clamps at 0
           float2 sc2[SPL];
 #pragma unroll
           for (int k = 0; k < SPL; ++k) sc2[k] = make_float2(0.f, 0.f);
@@ -495,7 +505,8 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
 #pragma unroll
           for (int k = 0; k < SPL; ++k) {
             fz[k] = OP ? feasible<ENV>(nG + k, (mybits >> k) & 1u, used + dist2_fma(lck[k], pcur), used, dmk[k], cur, depot_seen)
-                       : feasible<ENV>(nG + k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
+                    : PC ? feasible<ENV>(nG + k, (mybits >> k) & 1u, depot_seen ? 1.0f : 0.0f, used, thr, cur, nvis < N - 1)
+                         : feasible<ENV>(nG + k, (mybits >> k) & 1u, dmk[k], used, thr, cur, anyfeas);
             float dot = (sc2[k].x + sc2[k].y) + FK[k];
             if (VRP) dot = fmaf(rem, WK[k], dot);
             if (SD) dot = fmaf(dmk[k], qwk, dot);  // q . (K[n] + d_n wk) = q.K[n] + d_n (q.wk)
@@ -576,7 +587,8 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
         if (sel_warp) {
           // ---------------- pointer logit of node nL: heads summed in fixed order, tanh clip, mask, temperature
           const bool fzL = OP ? feasible<ENV>(nL, (mybits >> 8) & 1u, used + dist2_fma(lcL, sm.loc[cur]), used, dL, cur, depot_seen)
-                              : feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
+                           : PC ? feasible<ENV>(nL, (mybits >> 8) & 1u, depot_seen ? 1.0f : 0.0f, used, thr, cur, nvis < N - 1)
+                                : feasible<ENV>(nL, (mybits >> 8) & 1u, dL, used, thr, cur, anyfeas);
           const float p = ((sm.part[0][nL] + sm.part[1][nL]) + (sm.part[2][nL] + sm.part[3][nL])) +
                           ((sm.part[4][nL] + sm.part[5][nL]) + (sm.part[6][nL] + sm.part[7][nL]));
           const float lg = tanhf(p * 0.08838834764831845f) * clip;  // /sqrt(E), tanh clip (decoding.py:169-170)
@@ -632,7 +644,13 @@ __global__ void __launch_bounds__(256, Cfg<SPL>::MINB) rollout_kernel(const co_r
       if (tid == 0) {
         const float2 pa = sm.loc[(ENV == CO_ENV_TSP) ? first : 0], pp = sm.loc[prev];
         const float dx = pa.x - pp.x, dy = pa.y - pp.y;
-        A.reward_out[traj] = OP ? dist : -(dist + sqrtf(dx * dx + dy * dy));  // op: the collected prize
+        float rw = OP ? dist : -(dist + sqrtf(dx * dx + dy * dy));  // op: the collected prize
+        if (PC) {  // pctsp/env.py:153-172: saved penalties - (length + all penalties)
+          float total = 0.f;
+          for (int n = 1; n < N; ++n) total += sm.lim[n];
+          rw = pen - (-rw + total);
+        }
+        A.reward_out[traj] = rw;
         if (A.steps_out) A.steps_out[traj] = t;
         if (A.used_capacity_out) A.used_capacity_out[traj] = used;
         if (A.max_steps_out) atomicMax(A.max_steps_out, t);

@@ -267,6 +267,9 @@ class FusedAttentionModelDecoder(nn.Module):
                 w.dynamic_feature = feat.data_ptr()
             if self.env_name == "op":  # OPContext (context.py:201-213): [h_cur ; max_length[..., 0] - tour_length]
                 spent, budget = td["tour_length"].reshape(-1).contiguous(), td["max_length"][..., 0].reshape(-1).contiguous()
+            elif self.env_name == "pctsp":  # PCTSPContext (context.py:184-198): clamp(prize_required - collected, min=0)
+                budget = td["prize_required"].reshape(-1).contiguous()
+                spent = torch.minimum(td["cur_total_prize"].reshape(-1), budget).contiguous()
             else:                      # VRPContext (context.py:137-149): [h_cur ; vehicle_capacity - used_capacity]
                 spent, budget = td["used_capacity"].reshape(-1).contiguous(), td["vehicle_capacity"].reshape(-1).contiguous()
             logits = native.pointer_logits(

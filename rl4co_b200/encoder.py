@@ -67,6 +67,17 @@ def _train_attention_on(x, n_keys: int, num_heads: int) -> bool:
             and n_keys <= 128 and os.environ.get("CO_TRAIN_ATTN", "fused") != "sdpa")
 
 
+class PCTSPInitEmbedding(VRPInitEmbedding):
+    """init.py:221-251: depot (x, y); customers (x, y, expected prize, penalty)."""
+
+    def __init__(self, embed_dim, linear_bias=True):
+        super().__init__(embed_dim, linear_bias, node_dim=4)
+
+    @staticmethod
+    def _node_feature(td):
+        return torch.stack((td["expected_prize"], td["penalty"][..., 1:]), -1)
+
+
 class SkipConnection(nn.Module):
     def __init__(self, module):
         super().__init__()
@@ -158,7 +169,7 @@ class AttentionModelEncoder(nn.Module):
         self.env_name = env_name
         if init_embedding is None:
             init_embedding = {"tsp": TSPInitEmbedding, "cvrp": VRPInitEmbedding, "sdvrp": VRPInitEmbedding,
-                              "op": OPInitEmbedding}[env_name](embed_dim)
+                              "op": OPInitEmbedding, "pctsp": PCTSPInitEmbedding}[env_name](embed_dim)
         self.init_embedding = init_embedding
         self.net = GraphAttentionNetwork(num_heads, embed_dim, num_layers, normalization, feedforward_hidden) \
             if net is None else net

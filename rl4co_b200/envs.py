@@ -151,6 +151,38 @@ class OPGenerator(Generator, _DeviceStream):
                           batch_size=batch_size, device=dev)
 
 
+class PCTSPGenerator(Generator, _DeviceStream):
+    """rl4co/envs/routing/pctsp/generator.py:14-139: uniform locations (depot = first sampled point), penalties
+    U(0, max_penalty * penalty_factor / num_loc), deterministic prizes U(0, 4 / num_loc), stochastic prizes U(0, 2) x
+    deterministic -- sampled in that order.  `device="cuda"`: Philox streams of co_generate_uniform."""
+
+    def __init__(self, num_loc: int = 20, min_loc: float = 0.0, max_loc: float = 1.0, penalty_factor: float = 3.0,
+                 prize_required: float = 1.0, max_penalty: float | None = None, device=None, seed=None, **_):
+        self._init_stream(device, seed)
+        self.num_loc, self.min_loc, self.max_loc = num_loc, min_loc, max_loc
+        self.prize_required = prize_required
+        if max_penalty is None:
+            max_penalty = OP_MAX_LENGTHS.get(num_loc) or OP_MAX_LENGTHS[min(OP_MAX_LENGTHS, key=lambda x: abs(x - num_loc))]
+        self.max_penalty = max_penalty * penalty_factor / num_loc
+
+    def _generate(self, batch_size) -> TensorDict:
+        n = self.num_loc
+        if self.on_device:
+            off = self._next_offset(4)
+            u = lambda shape, k, hi: native.generate_uniform(shape, self.device, self.seed, off + k, 0.0, hi)  # noqa: E731
+            locs = native.generate_uniform((*batch_size, n + 1, 2), self.device, self.seed, off, self.min_loc, self.max_loc)
+            penalty, det, sto = u((*batch_size, n), 1, self.max_penalty), u((*batch_size, n), 2, 4.0 / n), u((*batch_size, n), 3, 2.0)
+            dev = self.device
+        else:
+            locs = torch.rand(*batch_size, n + 1, 2) * (self.max_loc - self.min_loc) + self.min_loc
+            penalty = torch.rand(*batch_size, n) * self.max_penalty
+            det = torch.rand(*batch_size, n) * (4.0 / n)
+            sto = torch.rand(*batch_size, n) * 2.0
+            dev = None
+        return TensorDict({"locs": locs[..., 1:, :], "depot": locs[..., 0, :], "penalty": penalty, "deterministic_prize": det,
+                           "stochastic_prize": sto * det}, batch_size=batch_size, device=dev)
+
+
 class FusedEnvBase:
     """Host-side mirror of RL4COEnvBase (rl4co/envs/common/base.py:19-333)."""
 
@@ -570,7 +602,92 @@ class FusedOPEnv(FusedEnvBase):
         assert (length[..., None] <= max_length + 1e-5).all(), "Max length exceeded"
 
 
-ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv, "sdvrp": FusedSDVRPEnv, "op": FusedOPEnv}
+class FusedPCTSPEnv(FusedEnvBase):
+    """CUDA drop-in for rl4co.envs.PCTSPEnv (rl4co/envs/routing/pctsp/env.py:18-264, prize-collecting TSP, deterministic
+    prizes): collect a total prize of at least 1 (or visit everything), then return to the depot; unvisited customers
+    cost their penalty.  State keys / dtypes as the reference's: `locs` [B,N,2], `current_node` [B], `expected_prize`
+    [B,N-1], `real_prize` / `penalty` [B,N] (depot 0), `cur_total_prize` / `cur_total_penalty` / `prize_required` [B],
+    `visited` bool [B,N], `i` [B].  Stepping kernels: co_pctsp_step / co_pctsp_action_mask; reward = co_op_reward over the
+    penalties + co_tour_length."""
+
+    name = "pctsp"
+
+    def __init__(self, generator=None, generator_params: dict | None = None, **kwargs):
+        super().__init__(**kwargs)
+        self.generator = PCTSPGenerator(**(generator_params or {})) if generator is None else generator
+
+    def _reset(self, td: TensorDict, batch_size=None) -> TensorDict:
+        """pctsp/env.py:95-141"""
+        device = td.device
+        prize, penalty = td["deterministic_prize"], td["penalty"]
+        td_reset = TensorDict(
+            {
+                "locs": torch.cat([td["depot"][..., None, :], td["locs"]], dim=-2),
+                "current_node": torch.zeros((*batch_size,), dtype=torch.int64, device=device),
+                "expected_prize": prize,
+                "real_prize": torch.cat([torch.zeros_like(prize[..., :1]), prize], dim=-1),
+                "penalty": torch.nn.functional.pad(penalty, (1, 0), mode="constant", value=0),
+                "cur_total_prize": torch.zeros(*batch_size, device=device),
+                "cur_total_penalty": penalty.sum(-1),
+                "visited": torch.zeros((*batch_size, td["locs"].shape[-2] + 1), dtype=torch.bool, device=device),
+                "prize_required": torch.full((*batch_size,), self.generator.prize_required, device=device),
+                "i": torch.zeros((*batch_size,), dtype=torch.int64, device=device),
+            },
+            batch_size=batch_size,
+        )
+        mask = torch.ones_like(td_reset["visited"])
+        mask[..., 0] = False  # nothing collected yet and customers remain (pctsp/env.py:143-151 at reset)
+        td_reset.set("action_mask", mask)
+        return td_reset
+
+    def _step(self, td: TensorDict) -> TensorDict:
+        """pctsp/env.py:62-93 incl. the trailing get_action_mask, one kernel (co_pctsp_step)."""
+        action = td["action"].contiguous()
+        B = action.shape[0]
+        vin = td["visited"].contiguous()
+        vout = vin if self.inplace else torch.empty_like(vin)
+        prize_sum, penalty_sum = td["cur_total_prize"].clone(), td["cur_total_penalty"].clone()
+        current_node, i = td["current_node"].reshape(B).clone(), td["i"].clone()
+        done = torch.empty(B, dtype=torch.bool, device=action.device)
+        mask_out = torch.empty(vin.shape, dtype=torch.bool, device=action.device)
+        native.pctsp_step(action, td["real_prize"].contiguous(), td["penalty"].contiguous(), vin, vout, prize_sum, penalty_sum,
+                          current_node, i, done, mask_out)
+        td.update({"current_node": current_node, "cur_total_prize": prize_sum, "cur_total_penalty": penalty_sum,
+                   "visited": vout, "i": i, "reward": torch.zeros_like(done), "done": done})
+        td.set("action_mask", mask_out)
+        return td
+
+    @staticmethod
+    def get_action_mask(td: TensorDict) -> torch.Tensor:
+        """pctsp/env.py:143-151 (co_pctsp_action_mask)"""
+        visited = td["visited"].contiguous()
+        mask = torch.empty(visited.shape, dtype=torch.bool, device=visited.device)
+        return native.pctsp_action_mask(visited, td["cur_total_prize"].contiguous(), mask)
+
+    def _get_reward(self, td: TensorDict, actions: torch.Tensor) -> torch.Tensor:
+        """pctsp/env.py:153-172: saved penalties - (tour length from / to the depot + all penalties)."""
+        if actions.size(-1) == 1:
+            assert (actions == 0).all(), "If all length 1 tours, they should be zero"
+            return torch.zeros(actions.size(0), dtype=torch.float, device=actions.device)
+        actions = actions.contiguous()
+        saved = native.op_reward(td["penalty"].contiguous(), actions)
+        neg_length = native.tour_length(td["locs"].contiguous(), actions, with_depot=True)
+        total = td["penalty"][..., 1:].sum(-1)
+        if total.shape[0] != saved.shape[0]:
+            total = total.repeat(saved.shape[0] // total.shape[0])
+        return saved - (-neg_length + total)
+
+    @staticmethod
+    def check_solution_validity(td: TensorDict, actions: torch.Tensor) -> None:
+        """pctsp/env.py:174-197: no customer twice; the prize constraint holds or every customer was visited."""
+        sorted_actions = actions.sort(1)[0]
+        assert ((sorted_actions[..., 1:] == 0) | (sorted_actions[..., 1:] > sorted_actions[..., :-1])).all(), "Duplicates"
+        p = native.op_reward(td["real_prize"].contiguous(), actions.contiguous())
+        all_visited = sorted_actions.size(-1) - (sorted_actions == 0).int().sum(-1) == (td["locs"].size(-2) - 1)
+        assert ((p >= 1 - 1e-5) | all_visited).all(), "Total prize does not satisfy min total prize"
+
+
+ENV_REGISTRY = {"tsp": FusedTSPEnv, "cvrp": FusedCVRPEnv, "sdvrp": FusedSDVRPEnv, "op": FusedOPEnv, "pctsp": FusedPCTSPEnv}
 
 
 def _register_with_torchrl() -> bool:

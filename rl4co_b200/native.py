@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcorollout.so")
-SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "rollout_op.cu", "gemm_tf32x3.cu",
+SOURCES = ["abi.cu", "env_kernels.cu", "decode_step.cu", "rollout.cu", "rollout_tsp.cu", "rollout_cvrp.cu", "rollout_ms_tsp.cu", "rollout_ms_cvrp.cu", "rollout_sdvrp.cu", "rollout_op.cu", "rollout_pctsp.cu", "gemm_tf32x3.cu",
            "encoder_mha.cu", "encoder_mha_tc.cu", "encoder_mha_tc2.cu", "encoder_mha_tc3.cu",
            "ffn_fused.cu", "data_kernels.cu", "attn_train.cu", "norm_kernels.cu", "op_kernels.cu"]
 HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
@@ -28,10 +28,10 @@ HEADERS = ["co_common.cuh", "rollout_impl.cuh", "rollout_ms_impl.cuh"]
 CO_OK = 0
 ENV_TSP, ENV_CVRP = 0, 1
 ENV_SDVRP = 2
-ENV_OP = 3
-ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP, "op": ENV_OP}
+ENV_OP, ENV_PCTSP = 3, 4
+ENV_KIND = {"tsp": ENV_TSP, "cvrp": ENV_CVRP, "sdvrp": ENV_SDVRP, "op": ENV_OP, "pctsp": ENV_PCTSP}
 #: environments the whole-episode kernel (co_rollout) is instantiated for; others take the stepping kernels
-ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp", "op")
+ROLLOUT_ENVS = ("tsp", "cvrp", "sdvrp", "op", "pctsp")
 SELECT_GREEDY, SELECT_SAMPLE_NOISE, SELECT_EVALUATE, SELECT_SAMPLE_PHILOX = 0, 1, 2, 3
 ROLLOUT_FORCED_START = 1
 EMBED_DIM, NUM_HEADS = 128, 8
@@ -41,7 +41,7 @@ EXPORTS = [
     "co_cvrp_step", "co_tour_length", "co_check_tours", "co_pointer_logits", "co_select_action",
     "co_cache_width", "co_rollout_max_nodes", "co_rollout", "co_reward_stats", "co_split_tf32", "co_gemm_tf32x3", "co_encoder_mha",
     "co_ffn_fused", "co_ffn_tile_weights", "co_ffn_tiled_weight_floats", "co_generate_uniform", "co_generate_demand", "co_dihedral8",
-    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd", "co_instance_norm", "co_op_step", "co_op_action_mask", "co_op_reward",
+    "co_sdvrp_step", "co_sdvrp_action_mask", "co_attn_fwd", "co_attn_bwd", "co_instance_norm", "co_op_step", "co_op_action_mask", "co_op_reward", "co_pctsp_step", "co_pctsp_action_mask",
 ]
 
 
@@ -146,6 +146,8 @@ def lib() -> ctypes.CDLL:
     L.co_reward_stats.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.co_op_action_mask.argtypes = [c_void_p] * 6 + [c_int, c_int, c_void_p]
     L.co_op_step.argtypes = [c_void_p] * 12 + [c_int, c_int, c_void_p]
+    L.co_pctsp_action_mask.argtypes = [c_void_p] * 3 + [c_int, c_int, c_void_p]
+    L.co_pctsp_step.argtypes = [c_void_p] * 11 + [c_int, c_int, c_void_p]
     L.co_op_reward.argtypes = [c_void_p] * 3 + [c_int, c_int, c_int, c_void_p]
     L.co_instance_norm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_float, c_void_p]
     L.co_attn_fwd.argtypes = [POINTER(AttnArgs), c_void_p]
@@ -309,6 +311,27 @@ def op_step(action, locs, prize, max_length, visited_in, visited_out, tour_lengt
 
 
 @_on_device_of_first_tensor
+def pctsp_action_mask(visited, cur_total_prize, mask_out):
+    """co_pctsp_action_mask (pctsp/env.py:143-151)."""
+    B, N = mask_out.shape
+    _check(lib().co_pctsp_action_mask(_bool_ptr(visited, "visited"), _ptr(cur_total_prize, F32, "cur_total_prize"),
+                                      _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_pctsp_action_mask")
+    return mask_out
+
+
+@_on_device_of_first_tensor
+def pctsp_step(action, real_prize, penalty, visited_in, visited_out, cur_total_prize, cur_total_penalty, current_node, i, done,
+               mask_out):
+    """co_pctsp_step (pctsp/env.py:62-93 + get_action_mask): prize / penalty sums, current_node, i in place."""
+    B, N = mask_out.shape
+    _check(lib().co_pctsp_step(_ptr(action, I64, "action"), _ptr(real_prize, F32, "real_prize"), _ptr(penalty, F32, "penalty"),
+                               _bool_ptr(visited_in, "visited_in"), _bool_ptr(visited_out, "visited_out"),
+                               _ptr(cur_total_prize, F32, "cur_total_prize"), _ptr(cur_total_penalty, F32, "cur_total_penalty"),
+                               _ptr(current_node, I64, "current_node"), _ptr(i, I64, "i"), _bool_ptr(done, "done"),
+                               _bool_ptr(mask_out, "mask_out"), B, N, _stream()), "co_pctsp_step")
+
+
+@_on_device_of_first_tensor
 def op_reward(prize, actions):
     """co_op_reward (op/env.py:157-165): prize [B_inst, N] (depot 0), actions [B, T] -> [B]; trajectory j uses instance
     j % B_inst."""
@@ -354,7 +377,7 @@ def pointer_logits(env_name, weights: DecoderWeights, node_emb, graph_ctx, K, V,
     logits = torch.empty(B_traj, N, dtype=F32, device=node_emb.device)
     # "op" shares the cvrp decoder arithmetic (context = [h_cur ; budget - spent], context.py:201-213): max_length[:, 0]
     # and tour_length stand in for vehicle_capacity and used_capacity
-    _check(lib().co_pointer_logits(ENV_KIND["cvrp" if env_name == "op" else env_name], ctypes.byref(weights), _ptr(node_emb, F32, "node_emb"),
+    _check(lib().co_pointer_logits(ENV_KIND["cvrp" if env_name in ("op", "pctsp") else env_name], ctypes.byref(weights), _ptr(node_emb, F32, "node_emb"),
                                    _ptr(graph_ctx, F32, "graph_ctx"), _ptr(K, F32, "glimpse_key", True),
                                    _ptr(V, F32, "glimpse_val", True), _ptr(L, F32, "logit_key", True),
                                    _bool_ptr(mask, "action_mask"), _ptr(first_node, I64, "first_node"),
@@ -552,7 +575,7 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
     S = max(1, int(num_starts))
     B_traj = B_inst * S
     if T_max is None:
-        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1}.get(env_name, 3 * (N - 1) + 2)
+        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1, "pctsp": N + 1}.get(env_name, 3 * (N - 1) + 2)
     actions = torch.empty(B_traj, T_max, dtype=I64, device=dev)
     logp = torch.empty(B_traj, T_max, dtype=F32, device=dev)
     reward = torch.empty(B_traj, dtype=F32, device=dev)
@@ -593,9 +616,9 @@ def rollout(env_name, select_mode, cache, graph_ctx, q_placeholder, w_capacity, 
         if dyn_w is None or tuple(dyn_w.shape) != (3 * EMBED_DIM,):
             raise ValueError("sdvrp needs dyn_w [3E] (dynamic-embedding weights, logit third folded)")
         a.dyn_w = _ptr(dyn_w, F32, "dyn_w")
-    if env_name == "op":
+    if env_name in ("op", "pctsp"):
         if node_limit is None or tuple(node_limit.shape) != (B_inst, N):
-            raise ValueError(f"op needs node_limit = max_length [{B_inst}, {N}]")
+            raise ValueError(f"{env_name} needs node_limit [{B_inst}, {N}] (op: max_length, pctsp: penalty)")
         a.node_limit = _ptr(node_limit, F32, "node_limit")
     if forced_actions is not None and tuple(forced_actions.shape) != (B_traj, T_max):
         raise ValueError(f"forced_actions must be [{B_traj}, {T_max}], got {tuple(forced_actions.shape)}")

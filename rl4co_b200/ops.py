@@ -58,7 +58,7 @@ def unbatchify_and_gather(x, idx, n: int):
 def get_num_starts(td, env_name=None) -> int:
     """rl4co/utils/ops.py:115-125 (tsp / cvrp / sdvrp / op rows)"""
     num_starts = td["action_mask"].shape[-1]
-    if env_name in ("cvrp", "sdvrp", "op"):
+    if env_name in ("cvrp", "sdvrp", "op", "pctsp"):
         num_starts -= 1
     return num_starts
 

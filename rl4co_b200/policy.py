@@ -133,7 +133,7 @@ class FusedAttentionModelPolicy(nn.Module):
         B_traj = B * S
         # decode-step bound: tsp N; cvrp 2(N-1) (every customer + a depot return each); sdvrp 3(N-1)+2 (a customer can
         # be split once per refill on top of that)
-        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1}.get(env_name, 3 * (N - 1) + 2)  # op: customers once + depot
+        T_max = {"tsp": N, "cvrp": 2 * (N - 1), "op": N + 1, "pctsp": N + 1}.get(env_name, 3 * (N - 1) + 2)  # op / pctsp: customers once + depot
         # S > 1 runs the query-batched kernel, which reads the tsp first-node table (one row per start)
         cached = self.decoder._precompute_cache(hidden, first_table=True if S > 1 else None)
 
@@ -168,7 +168,11 @@ class FusedAttentionModelPolicy(nn.Module):
             demand = td["prize"][..., 1:].contiguous()
             vcap = td["max_length"][..., 0].contiguous()
             node_limit = td["max_length"].contiguous()
-        num_loc = getattr(env.generator, "num_loc", N - (1 if vrp or env_name == "op" else 0))
+        elif env_name == "pctsp":  # real prizes in `demand`, prize_required in `vehicle_capacity`, penalties in `node_limit`
+            demand = td["real_prize"][..., 1:].contiguous()
+            vcap = td["prize_required"].reshape(-1).contiguous()
+            node_limit = td["penalty"].contiguous()
+        num_loc = getattr(env.generator, "num_loc", N - (1 if vrp or env_name in ("op", "pctsp") else 0))
         with torch.no_grad():
             res = native.rollout(
                 env_name, mode, cached.rollout_cache.detach().contiguous(), cached.graph_context_or_none,
@@ -199,7 +203,7 @@ class FusedAttentionModelPolicy(nn.Module):
                                                return_sum=False, temperature=temperature, tanh_clipping=tanh_clipping,
                                                forced_first=forced_start)
         if calc_reward and env.check_solution:
-            td_chk = td if S == 1 else TensorDict({k: td[k] for k in ("locs", "demand", "vehicle_capacity", "max_length")
+            td_chk = td if S == 1 else TensorDict({k: td[k] for k in ("locs", "demand", "vehicle_capacity", "max_length", "real_prize")
                                                    if k in td.keys()}, batch_size=td.batch_size)
             self._check(env, td_chk, out_actions.contiguous(), S)
         if S > 1 and select_best:  # decoding.py:415-423
@@ -214,7 +218,7 @@ class FusedAttentionModelPolicy(nn.Module):
 
     @staticmethod
     def _check(env, td, actions, S):
-        if env.name == "op":  # duplicates + length budget; rows of start-major trajectories share instances (j % B)
+        if env.name in ("op", "pctsp"):  # rows of start-major trajectories share instances (j % B)
             env.check_solution_validity(td, actions)
             return
         if env.name == "tsp":

@@ -62,7 +62,12 @@ def golden():
 
 
 def env_of(name):
-    return "tsp" if "tsp" in name else ("sdvrp" if "sdvrp" in name else ("op" if "_op" in name else "cvrp"))
+    for env in ("pctsp", "sdvrp", "cvrp"):
+        if env in name:
+            return env
+    if "_op" in name:
+        return "op"
+    return "tsp" if "tsp" in name else "cvrp"
 
 
 def name_seeded_weights(state_dict, seed):

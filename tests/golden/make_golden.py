@@ -45,6 +45,10 @@ def make_env(name, n, check=True):
         import importlib
 
         Env = importlib.import_module("rl4co.envs.routing.op.env").OPEnv
+    elif name == "pctsp":
+        import importlib
+
+        Env = importlib.import_module("rl4co.envs.routing.pctsp.env").PCTSPEnv
     else:
         Env = ref.TSPEnv if name == "tsp" else ref.CVRPEnv
     if name == "op":
@@ -79,6 +83,9 @@ def env_fixture(name, n, batch, seed):
         if name == "op":
             visited.append(npy(td["visited"]))
             used.append(np.stack([npy(td["tour_length"]), npy(td["current_total_prize"])]))
+        if name == "pctsp":
+            visited.append(npy(td["visited"]))
+            used.append(np.stack([npy(td["cur_total_prize"]), npy(td["cur_total_penalty"])]))
     actions = torch.stack(actions, 1)
     reward = env.get_reward(td, actions)  # runs check_solution_validity too
     out.update(actions=npy(actions), action_mask=np.stack(masks), done=np.stack(dones),
@@ -90,6 +97,9 @@ def env_fixture(name, n, batch, seed):
     elif name == "op":
         st = np.stack(used)  # [T, 2, B]
         out.update(visited=np.stack(visited), tour_length=st[:, 0], current_total_prize=st[:, 1])
+    elif name == "pctsp":
+        st = np.stack(used)
+        out.update(visited=np.stack(visited), cur_total_prize=st[:, 0], cur_total_penalty=st[:, 1])
     else:
         out.update(first_node=npy(td["first_node"]), i=npy(td["i"]))
     return out
@@ -376,6 +386,10 @@ def main():
         "env_op50": lambda: env_fixture("op", 50, 8, 109),
         "am_op20": lambda: sdvrp_am_fixture(20, 8, 210, name="op"),
         "am_op50": lambda: sdvrp_am_fixture(50, 4, 211, name="op"),
+        "env_pctsp20": lambda: env_fixture("pctsp", 20, 16, 110),
+        "env_pctsp50": lambda: env_fixture("pctsp", 50, 8, 111),
+        "am_pctsp20": lambda: sdvrp_am_fixture(20, 8, 212, name="pctsp"),
+        "am_pctsp50": lambda: sdvrp_am_fixture(50, 4, 213, name="pctsp"),
         "enc_tsp20_batch": lambda: encoder_fixture("tsp", 20, 4, 300, "batch"),
         "enc_cvrp20_instance": lambda: encoder_fixture("cvrp", 20, 4, 301, "instance"),
         "layout": layout_fixture,

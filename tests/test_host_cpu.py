@@ -121,7 +121,7 @@ def test_generators_match_reference_call_order():
     from oracle import am_rollout_oracle as O
     from rl4co_b200.envs import get_env
 
-    for name, n in (("tsp", 50), ("cvrp", 50), ("cvrp", 100), ("op", 20), ("op", 50)):
+    for name, n in (("tsp", 50), ("cvrp", 50), ("cvrp", 100), ("op", 20), ("op", 50), ("pctsp", 20), ("pctsp", 100)):
         env = get_env(name, generator_params=dict(num_loc=n))
         torch.manual_seed(1234)
         td = env.generator(6)
@@ -236,7 +236,7 @@ def test_unsupported_options_are_rejected():
     with pytest.raises(NotImplementedError):
         FusedAttentionModelDecoder(embed_dim=256)
     with pytest.raises(NotImplementedError):
-        FusedAttentionModelDecoder(env_name="pctsp")
+        FusedAttentionModelDecoder(env_name="cvrptw")
     with pytest.raises(NotImplementedError):
         get_decoding_strategy("lookahead")
     with pytest.raises(AssertionError):

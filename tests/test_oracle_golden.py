@@ -7,9 +7,9 @@ import torch
 from oracle import am_rollout_oracle as O
 from conftest import env_of
 
-ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50", "env_sdvrp20", "env_sdvrp50", "env_op20", "env_op50"]
+ENV_FIX = ["env_tsp20", "env_tsp50", "env_cvrp20", "env_cvrp50", "env_sdvrp20", "env_sdvrp50", "env_op20", "env_op50", "env_pctsp20", "env_pctsp50"]
 AM_FIX = ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50", "am_tsp100", "am_cvrp100"]
-SD_FIX = ["am_sdvrp20", "am_sdvrp50", "am_op20", "am_op50"]  # sibling envs (sdvrp: dynamic embedding; op), single start
+SD_FIX = ["am_sdvrp20", "am_sdvrp50", "am_op20", "am_op50", "am_pctsp20", "am_pctsp50"]  # sibling envs (sdvrp: dynamic embedding; op), single start
 
 
 @pytest.mark.parametrize("name", ENV_FIX)
@@ -34,6 +34,10 @@ def test_env_mdp_bit_exact(golden, name):
             assert torch.equal(st["visited"], g["visited"][t].bool())
             assert torch.equal(st["tour_length"], g["tour_length"][t])
             assert torch.equal(st["current_total_prize"], g["current_total_prize"][t])
+        if env == "pctsp":
+            assert torch.equal(st["visited"], g["visited"][t].bool())
+            assert torch.equal(st["cur_total_prize"], g["cur_total_prize"][t])
+            assert torch.equal(st["cur_total_penalty"], g["cur_total_penalty"][t])
     if env == "tsp":
         assert torch.equal(st["first_node"], g["first_node"])
         assert torch.equal(st["i"], g["i"])
@@ -42,6 +46,8 @@ def test_env_mdp_bit_exact(golden, name):
         O.sdvrp_check_solution(st, actions)
     elif env == "op":
         O.op_check_solution(st, actions)
+    elif env == "pctsp":
+        O.pctsp_check_solution(st, actions)
     else:
         O.cvrp_check_solution(st, actions)
     r = O.env_reward(env, st, actions)
@@ -194,10 +200,12 @@ def test_pomo_config_c4_fixture(golden):
     torch.testing.assert_close(max_aug, g["max_aug_reward"])
 
 
-@pytest.mark.parametrize("name", ["am_op20", "am_op50"])
+@pytest.mark.parametrize("name", ["am_op20", "am_op50", "am_pctsp20", "am_pctsp50"])
 def test_op_encoder_from_instance(golden, name):
-    """OPInitEmbedding (init.py:254-280: depot / (x, y, prize)) + one encoder layer reproduce the recorded embeddings."""
+    """OPInitEmbedding (init.py:254-280: depot / (x, y, prize)) and PCTSPInitEmbedding (init.py:221-251: (x, y, expected
+    prize, penalty)) + one encoder layer reproduce the recorded embeddings."""
     g = golden(name)
-    st = O.env_reset("op", g.inst())
-    h, _ = O.encoder_forward(g.weights(), "op", st, num_layers=1, normalization="batch")
+    env = env_of(name)
+    st = O.env_reset(env, g.inst())
+    h, _ = O.encoder_forward(g.weights(), env, st, num_layers=1, normalization="batch")
     torch.testing.assert_close(h, g["h"], rtol=1e-5, atol=1e-5)
