@@ -25,7 +25,7 @@ def t(fn, n=3):
     return e0.elapsed_time(e1) / n, out
 
 
-for env_name in ("cvrp", "sdvrp", "op"):
+for env_name in ("cvrp", "sdvrp", "op", "pctsp"):
     torch.manual_seed(0)
     env = get_env(env_name, generator_params=dict(num_loc=N), check_solution=False)
     pol = FusedAttentionModelPolicy(env_name=env_name).to(dev).eval()

@@ -35,9 +35,15 @@ print("gemm ok")
 env = get_env("op", generator_params=dict(num_loc=20), check_solution=True)
 pol = FusedAttentionModelPolicy(env_name="op", num_encoder_layers=1).to(dev).eval()
 with torch.inference_mode():
-    for dt in ("greedy", "sampling"):
-        out = pol(env.reset(env.generator(300).to(dev)), env, decode_type=dt)
+    for kw in (dict(decode_type="greedy"), dict(decode_type="sampling"), dict(decode_type="sampling", fused_rollout=False)):
+        out = pol(env.reset(env.generator(300).to(dev)), env, **kw)
 print("op ok", out["reward"].mean().item())
+env = get_env("pctsp", generator_params=dict(num_loc=20), check_solution=True)
+pol = FusedAttentionModelPolicy(env_name="pctsp", num_encoder_layers=1).to(dev).eval()
+with torch.inference_mode():
+    for kw in (dict(decode_type="greedy"), dict(decode_type="sampling"), dict(decode_type="sampling", fused_rollout=False)):
+        out = pol(env.reset(env.generator(300).to(dev)), env, **kw)
+print("pctsp ok", out["reward"].mean().item())
 # training-step attention kernels (forward, dQ, dK/dV) with a mask and strided key / value views; instance norm
 from rl4co_b200 import attention_train as AT
 
