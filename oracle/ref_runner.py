@@ -165,13 +165,16 @@ def time_reference(env_name, num_loc, batch, decode_type, steps=2, warmup=1, pol
     if multi_process and cores >= 16:
         T = 16 if cores >= 32 else 8
         P = max(1, cores // T)
-        procs = [_spawn(env_name, num_loc, batch, decode_type, steps, warmup, T, 1234 + i, policy_kwargs,
+        # bounded: half the per-process sample and at most two timed passes -- on a loaded 128-core host one pass of
+        # 8 x 1 024 TSP-100 instances took 51 s, and the leg must stay within "10-30 s of CPU work per measurement"
+        m_batch, m_steps = max(min(batch, 128), batch // 2), min(steps, 2)
+        procs = [_spawn(env_name, num_loc, m_batch, decode_type, m_steps, warmup, T, 1234 + i, policy_kwargs,
                         decode_kwargs, augment, train) for i in range(P)]
         outs = _collect(procs)
         # every worker runs the same amount of work concurrently: aggregate = total / slowest worker's timed span
         span = max(sum(o["step_s"]) for o in outs)
         res["multi"] = {"processes": P, "threads_each": T, "value": sum(o["selections"] for o in outs) / span,
-                        "ms_per_step": 1e3 * span / steps, "batch": batch * P}
+                        "ms_per_step": 1e3 * span / m_steps, "batch": m_batch * P}
     best = res["single"]
     res["layout"] = f"1 process x {best_t} threads"
     res["cores_used"] = best_t
