@@ -203,8 +203,8 @@ def test_pctsp_under_the_reference_loop():
     from rl4co_b200.decoder import FusedAttentionModelDecoder
     from rl4co_b200.envs import get_env
 
-    OPEnv = importlib.import_module("rl4co.envs.routing.pctsp.env").PCTSPEnv
-    env_ref = OPEnv(generator_params=dict(num_loc=20), check_solution=True)
+    PCTSPEnv = importlib.import_module("rl4co.envs.routing.pctsp.env").PCTSPEnv
+    env_ref = PCTSPEnv(generator_params=dict(num_loc=20), check_solution=True)
     env_fused = get_env("pctsp", generator_params=dict(num_loc=20), check_solution=True)
     torch.manual_seed(3)
     pure = ref.AttentionModelPolicy(env_name="pctsp", num_encoder_layers=1).to(DEV).eval()

@@ -13,7 +13,11 @@ __global__ void k(int pattern, int stride_b, float* out, long long* cyc) {
   else if (pattern == 3) sel = (lane >> 3) & 1;  // quarter warps alternate
   else if (pattern == 4) sel = lane & 3;   // four chunks, alternating
   else if (pattern == 5) sel = lane >> 3;  // four chunks, quarter warps
-  uint32_t addr = (uint32_t)__cvta_generic_to_shared(buf) + sel * stride_b;
+  // chunk `sel` of instruction c: far-apart chunks (stride_b = 272 B, the padded layout of the kernel) advance by 16 B per
+  // instruction; adjacent chunks (stride_b = 16) are interleaved, so an instruction's group of chunks advances as a whole
+  const int groups = (pattern == 4 || pattern == 5) ? 4 : (pattern == 0 ? 1 : 2);
+  const uint32_t step = (stride_b == 16) ? 16u * groups : 16u;
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(buf) + sel * stride_b;
   float4 acc = make_float4(0, 0, 0, 0);
   __syncthreads();
   long long t0 = clock64();
@@ -22,7 +26,7 @@ __global__ void k(int pattern, int stride_b, float* out, long long* cyc) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       float4 v;
-      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + c * 16 * (pattern == 6 ? 0 : 1) * ((stride_b == 16 || stride_b == 32) ? (stride_b == 16 ? 2 : 4) : 1)));
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + c * step));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
