@@ -80,15 +80,18 @@ def get_tour_length(ordered_locs):
     return (nxt - ordered_locs).norm(p=2, dim=-1).sum(-1)
 
 
+DEPOT_ENVS = ("cvrp", "sdvrp", "op", "pctsp")
+
+
 def get_num_starts(num_actions: int, env_name: str) -> int:
-    """rl4co/utils/ops.py:115-125"""
-    return num_actions - 1 if env_name == "cvrp" else num_actions
+    """rl4co/utils/ops.py:115-125 (depot envs: the depot is not a start node)"""
+    return num_actions - 1 if env_name in DEPOT_ENVS else num_actions
 
 
 def select_start_nodes(batch: int, num_starts: int, num_loc: int, env_name: str, device=None):
     """rl4co/utils/ops.py:128-149. ``num_loc`` = generator.num_loc (customers for CVRP)."""
     sel = torch.arange(num_starts, device=device).repeat_interleave(batch) % num_loc
-    return sel + 1 if env_name == "cvrp" else sel
+    return sel + 1 if env_name in DEPOT_ENVS else sel  # (op's resampling branch, ops.py:150-160, is not restated)
 
 
 def dihedral_8_augmentation(xy):
@@ -674,7 +677,7 @@ def rollout(weights, env_name, inst, h, decode_type="greedy", num_starts=None, a
     if multistart:
         S = num_starts if num_starts is not None else get_num_starts(st["action_mask"].shape[-1], env_name)
         if S > 1 or num_starts is None:
-            nl = num_loc if num_loc is not None else (st["locs"].shape[1] - (1 if env_name == "cvrp" else 0))
+            nl = num_loc if num_loc is not None else (st["locs"].shape[1] - (1 if env_name in DEPOT_ENVS else 0))
             a0 = select_start_nodes(B, S, nl, env_name, device=st["locs"].device)
             st = {k: batchify(v, S) for k, v in st.items()}
             st = step_fn(st, a0)

@@ -118,3 +118,29 @@ def test_generator_matches_reference(ref):
         inst = O.generate_instances(name, 5, n)
         for k in inst:
             assert torch.equal(td[k], inst[k]), (name, k)
+
+
+@pytest.mark.parametrize("name,n", [("op", 20), ("op", 33), ("pctsp", 20), ("pctsp", 41), ("sdvrp", 20)])
+@pytest.mark.parametrize("decode_type", ["greedy", "sampling"])
+def test_sibling_env_policy_forward_matches_reference(ref, name, n, decode_type):
+    """The sibling envs on fresh seeds: the live reference policy (its own env, init / context / dynamic
+    embeddings) against the oracle's restatement -- actions bit for bit, rewards and log-likelihoods to 1e-5."""
+    import importlib
+
+    torch.manual_seed(2000 + n)
+    cls = {"op": "OPEnv", "pctsp": "PCTSPEnv", "sdvrp": "SDVRPEnv"}[name]
+    Env = getattr(importlib.import_module(f"rl4co.envs.routing.{name}.env"), cls)
+    gp = dict(num_loc=n, prize_distribution="dist") if name == "op" else dict(num_loc=n)  # see make_golden.make_env
+    env = Env(generator_params=gp, check_solution=True)
+    pol = ref.AttentionModelPolicy(env_name=name, num_encoder_layers=2).eval()
+    W = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    td0 = env.generator(batch_size=[8])
+    inst = {k: td0[k].clone() for k in td0.keys()}
+    with torch.inference_mode():
+        torch.manual_seed(5)
+        out = pol(env.reset(td0.clone()), env, phase="test", decode_type=decode_type)
+        torch.manual_seed(5)
+        o = O.policy_forward(W, name, inst, decode_type=decode_type, num_layers=2)
+    assert torch.equal(out["actions"], o["actions"])
+    torch.testing.assert_close(out["reward"], o["reward"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out["log_likelihood"], o["log_likelihood"], rtol=1e-5, atol=1e-5)
