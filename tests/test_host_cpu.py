@@ -363,3 +363,34 @@ def test_seeded_dataset_generation_matches_reference(tmp_path):
     np.testing.assert_allclose(ds[0]["demand"].numpy(), raw["demand"][0] / raw["capacity"][0])  # cvrp/env.py:179-186
     assert len(env.dataset(batch_size=[5], phase="train")) == 5          # no train file: generated
     assert len(env.dataset(batch_size=[7], phase="test")) == 7           # test file unset: generated
+
+
+@pytest.mark.parametrize("name", ["am_tsp20", "am_cvrp20", "am_tsp50", "am_cvrp50"])
+def test_teacher_forced_pass_matches_reference_logprobs_cpu(golden, name):
+    """The vectorised teacher-forced pass of the training step (replay of the MDP without a time loop + one batched
+    attention over all decode steps) is plain torch off the GPU: its per-step log-probabilities along the reference's
+    recorded trajectories equal the log-probabilities the reference recorded step by step
+    (models/common/constructive/base.py:176-238 with `actions=`; multistart: decoding.py:300-345)."""
+    from conftest import env_of
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+    from rl4co_b200.reinforce import evaluate_log_likelihood
+    from rl4co_b200.tensordict import TensorDict
+
+    g = golden(name)
+    env_name = env_of(name)
+    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=1).eval()
+    pol.load_state_dict({**pol.state_dict(), **g.weights()})
+    inst, h = g.inst(), g["h"]
+    B = h.shape[0]
+    env = get_env(env_name, generator_params=dict(num_loc=inst["locs"].shape[1]))
+    td = env.reset(TensorDict(inst, batch_size=[B]))
+    for mode in ("greedy", "sampling", "eval"):
+        lp = evaluate_log_likelihood(pol, td, env, g[f"{mode}_actions"], hidden=h, return_sum=False)
+        torch.testing.assert_close(lp, g[f"{mode}_logprobs"], rtol=1e-5, atol=2e-5)
+        assert lp.requires_grad
+    mb = int(g["ms_batch"])
+    tdm = env.reset(TensorDict({k: v[:mb] for k, v in inst.items()}, batch_size=[mb]))
+    lp = evaluate_log_likelihood(pol, tdm, env, g["ms_actions"], hidden=h[:mb], return_sum=False)
+    torch.testing.assert_close(lp, g["ms_logprobs"], rtol=1e-5, atol=2e-5)
+    assert (lp[:, 0] == 0).all()   # the forced start node carries no log-probability
