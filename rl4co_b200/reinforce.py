@@ -63,6 +63,60 @@ def replay_states(env_name: str, td: TensorDict, actions: torch.Tensor):
     return ~torch.cat([mask_depot, mask_loc], -1), prev, None, used
 
 
+def _running_total_before(step_values: torch.Tensor) -> torch.Tensor:
+    """[B,T] per-step increments -> [B,T] totals BEFORE each step, accumulated one step after the other in fp32 exactly
+    like the env's own `total = total + increment` (a parallel scan rounds differently, and the op length test below
+    compares the total against a bound)."""
+    total = torch.zeros_like(step_values[:, 0])
+    cols = []
+    for t in range(step_values.shape[1]):
+        cols.append(total)
+        total = total + step_values[:, t]
+    return torch.stack(cols, 1)
+
+
+def replay_budget_states(env_name: str, td: TensorDict, actions: torch.Tensor):
+    """Replay of the orienteering / prize-collecting MDPs along given actions [B,T]: returns (mask [B,T,N] bool,
+    cur [B,T] node before step t, state [B,T] = the scalar the context embedding appends to h_cur before step t:
+    op `max_length[0] - tour_length` (context.py:201-213), pctsp `clamp(prize_required - cur_total_prize, 0)`
+    (context.py:184-198)).  Restates op/env.py:72-155 and pctsp/env.py:62-151; the only time loop is the running
+    fp32 total of one scalar per instance.  Columns after an instance is done hold depot actions whose mask leaves
+    the depot alone (log-probability 0), as in the reference's padded decode loop."""
+    B, T = actions.shape
+    locs = td["locs"]
+    N = locs.shape[-2]
+    dev = actions.device
+    onehot = torch.zeros(B, T, N, dtype=torch.uint8, device=dev).scatter_(2, actions.unsqueeze(-1), 1)
+    visited_before = torch.cat([torch.zeros(B, 1, N, dtype=torch.uint8, device=dev),
+                                onehot[:, :-1].cummax(1)[0]], 1).bool()
+    prev = torch.cat([torch.zeros(B, 1, dtype=actions.dtype, device=dev), actions[:, :-1]], 1)
+    closed = visited_before[..., 0:1]                # the depot was chosen before step t: no customer may follow
+    if env_name == "op":
+        pts = gather_by_index(locs, actions)                                           # [B,T,2]
+        leg = (pts - torch.cat([locs[:, 0:1], pts[:, :-1]], 1)).norm(p=2, dim=-1)      # op/env.py:80-84
+        length_before = _running_total_before(leg)
+        # |locs[n] - locs[cur]| for every n: row `cur` of the pairwise matrix (the sign of the difference is squared away)
+        pair = (locs[:, :, None, :] - locs[:, None, :, :]).norm(p=2, dim=-1)           # [B,N,N]
+        dist = pair.gather(1, prev[..., None].expand(B, T, N))
+        exceeds = length_before[..., None] + dist > td["max_length"][:, None, :]       # op/env.py:146-149
+        mask = ~(visited_before | closed | exceeds)
+        mask[..., 0] = True
+        # the actions come from a rollout that found them feasible; should a length sum ever round differently here
+        # than in the kernel that produced them, the chosen node must not end up with log-probability -inf
+        mask.scatter_(2, actions.unsqueeze(-1), True)
+        return mask, prev, td["max_length"][:, 0:1] - length_before
+    if env_name == "pctsp":
+        prize_before = _running_total_before(td["real_prize"].gather(1, actions))      # pctsp/env.py:66-68
+        customers_left = visited_before[..., 1:].sum(-1) < N - 1
+        depot_ok = ~((prize_before < 1.0) & customers_left)                            # pctsp/env.py:147-149
+        mask = torch.cat([depot_ok[..., None], ~(visited_before | closed)[..., 1:]], -1)
+        return mask, prev, torch.clamp(td["prize_required"][:, None] - prize_before, min=0)
+    raise NotImplementedError(env_name)
+
+
+REPLAY_KEYS = ("locs", "demand", "vehicle_capacity", "max_length", "real_prize", "prize_required")
+
+
 def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, hidden=None,
                             return_sum: bool = True, temperature=None, tanh_clipping=None,
                             forced_first=None) -> torch.Tensor:
@@ -70,9 +124,11 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     kernel reported for the same actions.  `td` is the reset state (multistart: the [B] state,
     actions [S*B, T] in the reference's start-major order)."""
     env_name = env.name
-    if env_name not in ("tsp", "cvrp"):
-        raise NotImplementedError(f"the vectorised teacher-forced pass replays tsp / cvrp state only (got {env_name!r}); "
-                                  "use policy(td, env, actions=...) on the stepping kernels for evaluation")
+    if env_name not in ("tsp", "cvrp", "op", "pctsp"):
+        # sdvrp: the glimpse keys / values change every step (dynamic embedding), which this one-attention-call form
+        # cannot express
+        raise NotImplementedError(f"the vectorised teacher-forced pass replays tsp / cvrp / op / pctsp state only (got "
+                                  f"{env_name!r}); use policy(td, env, actions=...) on the stepping kernels for evaluation")
     dec = policy.decoder
     if hidden is None:
         hidden, _ = policy.encoder(td)
@@ -87,9 +143,11 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     acts = actions.view(S, B, T).permute(1, 0, 2).reshape(B * S, T) if S > 1 else actions   # instance-major
     tdx = td
     if S > 1:
-        tdx = TensorDict({k: td[k].repeat_interleave(S, 0) for k in ("locs", "demand", "vehicle_capacity") if k in td.keys()},
-                         batch_size=[B * S])
-    mask, prev, first, used = replay_states(env_name, tdx, acts)
+        tdx = TensorDict({k: td[k].repeat_interleave(S, 0) for k in REPLAY_KEYS if k in td.keys()}, batch_size=[B * S])
+    if env_name in ("op", "pctsp"):
+        mask, prev, state = replay_budget_states(env_name, tdx, acts)
+    else:
+        mask, prev, first, used = replay_states(env_name, tdx, acts)
     Q = S * T
     mask = mask.view(B, Q, N)
     prev_q = prev.reshape(B, Q)
@@ -103,9 +161,9 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
             q0 = F.linear(dec.context_embedding.W_placeholder, wc)
             q = torch.cat([q0.expand(B, 1, E), q[:, 1:]], 1)
     else:
-        cap = tdx["vehicle_capacity"].reshape(B * S, 1)
-        rem = (cap - used).reshape(B, Q, 1)
-        q = F.linear(torch.cat([gather_by_index(hidden, prev_q), rem], -1), wc)                                  # [B,Q,E]
+        if env_name == "cvrp":
+            state = tdx["vehicle_capacity"].reshape(B * S, 1) - used
+        q = F.linear(torch.cat([gather_by_index(hidden, prev_q), state.reshape(B, Q, 1)], -1), wc)               # [B,Q,E]
     if g is not None:
         q = q + g[:, None, :]
     H = native.NUM_HEADS

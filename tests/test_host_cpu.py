@@ -394,3 +394,49 @@ def test_teacher_forced_pass_matches_reference_logprobs_cpu(golden, name):
     lp = evaluate_log_likelihood(pol, tdm, env, g["ms_actions"], hidden=h[:mb], return_sum=False)
     torch.testing.assert_close(lp, g["ms_logprobs"], rtol=1e-5, atol=2e-5)
     assert (lp[:, 0] == 0).all()   # the forced start node carries no log-probability
+
+
+@pytest.mark.parametrize("name", ["am_op20", "am_op50", "am_pctsp20", "am_pctsp50"])
+def test_teacher_forced_pass_budget_envs_cpu(golden, name):
+    """Orienteering / prize-collecting TSP: the replay of tour length / collected prize without the env (one fp32
+    running total per instance) gives the reference's masks bit for bit, and the one-call teacher-forced pass the
+    reference's recorded log-probabilities; longer near-uniform trajectories are checked against the oracle."""
+    from conftest import env_of
+    from oracle import am_rollout_oracle as O
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+    from rl4co_b200.reinforce import evaluate_log_likelihood, replay_budget_states
+    from rl4co_b200.tensordict import TensorDict
+
+    g = golden(name)
+    env_name = env_of(name)
+    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=1).eval()
+    pol.load_state_dict({**pol.state_dict(), **g.weights()})
+    inst, h = g.inst(), g["h"]
+    B = h.shape[0]
+    gp = dict(num_loc=inst["locs"].shape[1])
+    if env_name == "op":
+        gp["prize_type"] = "dist"
+    env = get_env(env_name, generator_params=gp)
+    td = env.reset(TensorDict(inst, batch_size=[B]))
+    for mode in ("greedy", "sampling", "eval"):
+        lp = evaluate_log_likelihood(pol, td, env, g[f"{mode}_actions"], hidden=h, return_sum=False)
+        torch.testing.assert_close(lp, g[f"{mode}_logprobs"], rtol=1e-5, atol=2e-5)
+    mask, _, _ = replay_budget_states(env_name, td, g["greedy_actions"])
+    assert torch.equal(mask.transpose(0, 1), g["greedy_masks"].bool())
+    # near-uniform random feasible tours from the oracle (temperature 50), many instances: every mask and log-prob
+    gen = torch.Generator().manual_seed(11)
+    inst2 = O.generate_instances(env_name, 96, gp["num_loc"], generator=gen)
+    w = g.weights()
+    h2 = torch.randn(96, gp["num_loc"] + 1, 128, generator=gen)   # any node embeddings do: the decoder is under test
+    with torch.no_grad():
+        ref = O.rollout(w, env_name, inst2, h2, decode_type="sampling", temperature=50.0, generator=gen, return_trace=True)
+    assert ref["actions"].shape[1] > 5
+    td2 = env.reset(TensorDict(inst2, batch_size=[96]))
+    mask, _, _ = replay_budget_states(env_name, td2, ref["actions"])
+    assert torch.equal(mask, torch.stack(ref["trace"]["mask"], 1))
+    lp = evaluate_log_likelihood(pol, td2, env, ref["actions"], hidden=h2.clone().requires_grad_(), return_sum=False,
+                                 temperature=50.0)
+    torch.testing.assert_close(lp, ref["logprobs"], rtol=1e-5, atol=2e-5)
+    lp.sum().backward()   # the graph reaches the decoder weights
+    assert pol.decoder.context_embedding.project_context.weight.grad.abs().sum() > 0
