@@ -114,6 +114,31 @@ def replay_budget_states(env_name: str, td: TensorDict, actions: torch.Tensor):
     raise NotImplementedError(env_name)
 
 
+def replay_split_delivery_states(td: TensorDict, actions: torch.Tensor):
+    """Replay of the split-delivery MDP (sdvrp/env.py:55-116) along given actions [B,T]: returns (mask [B,T,N] bool,
+    cur [B,T], used [B,T] capacity before step t, remaining [B,T,N] node-indexed demand before step t).  What a visit
+    delivers depends on what every earlier visit left, so this one is a time loop of [B]-sized gathers / scatters in
+    the env's own fp32 arithmetic."""
+    B, T = actions.shape
+    dev = actions.device
+    cap = td["vehicle_capacity"].reshape(B)
+    remaining = torch.cat([torch.zeros(B, 1, device=dev), td["demand"]], 1)
+    used = torch.zeros(B, device=dev)
+    rem_cols, used_cols = [], []
+    for t in range(T):
+        rem_cols.append(remaining)
+        used_cols.append(used)
+        a = actions[:, t:t + 1]
+        delivered = torch.min(remaining.gather(1, a).squeeze(1), cap - used)
+        used = (used + delivered) * (a.squeeze(1) != 0).float()
+        remaining = remaining.scatter_add(1, a, -delivered[:, None])
+    remaining, used = torch.stack(rem_cols, 1), torch.stack(used_cols, 1)
+    prev = torch.cat([torch.zeros(B, 1, dtype=actions.dtype, device=dev), actions[:, :-1]], 1)
+    mask_loc = (remaining[..., 1:] == 0) | (used >= cap[:, None])[..., None]           # sdvrp/env.py:110-116
+    mask_depot = (prev == 0) & ((~mask_loc).sum(-1) > 0)
+    return ~torch.cat([mask_depot[..., None], mask_loc], -1), prev, used, remaining
+
+
 REPLAY_KEYS = ("locs", "demand", "vehicle_capacity", "max_length", "real_prize", "prize_required")
 
 
@@ -124,11 +149,9 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     kernel reported for the same actions.  `td` is the reset state (multistart: the [B] state,
     actions [S*B, T] in the reference's start-major order)."""
     env_name = env.name
-    if env_name not in ("tsp", "cvrp", "op", "pctsp"):
-        # sdvrp: the glimpse keys / values change every step (dynamic embedding), which this one-attention-call form
-        # cannot express
-        raise NotImplementedError(f"the vectorised teacher-forced pass replays tsp / cvrp / op / pctsp state only (got "
-                                  f"{env_name!r}); use policy(td, env, actions=...) on the stepping kernels for evaluation")
+    if env_name not in ("tsp", "cvrp", "sdvrp", "op", "pctsp"):
+        raise NotImplementedError(f"the vectorised teacher-forced pass replays tsp / cvrp / sdvrp / op / pctsp state only "
+                                  f"(got {env_name!r}); use policy(td, env, actions=...) on the stepping kernels")
     dec = policy.decoder
     if hidden is None:
         hidden, _ = policy.encoder(td)
@@ -144,11 +167,16 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
     tdx = td
     if S > 1:
         tdx = TensorDict({k: td[k].repeat_interleave(S, 0) for k in REPLAY_KEYS if k in td.keys()}, batch_size=[B * S])
+    Q = S * T
+    remaining = None
     if env_name in ("op", "pctsp"):
         mask, prev, state = replay_budget_states(env_name, tdx, acts)
+    elif env_name == "sdvrp":
+        mask, prev, used, remaining = replay_split_delivery_states(tdx, acts)
+        remaining = remaining.reshape(B, Q, N).clone()
+        remaining[..., 0] = 0                                      # dynamic.py:71-73: the depot's feature is forced to 0
     else:
         mask, prev, first, used = replay_states(env_name, tdx, acts)
-    Q = S * T
     mask = mask.view(B, Q, N)
     prev_q = prev.reshape(B, Q)
     wc = dec.context_embedding.project_context.weight
@@ -161,7 +189,7 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
             q0 = F.linear(dec.context_embedding.W_placeholder, wc)
             q = torch.cat([q0.expand(B, 1, E), q[:, 1:]], 1)
     else:
-        if env_name == "cvrp":
+        if env_name in ("cvrp", "sdvrp"):
             state = tdx["vehicle_capacity"].reshape(B * S, 1) - used
         q = F.linear(torch.cat([gather_by_index(hidden, prev_q), state.reshape(B, Q, 1)], -1), wc)               # [B,Q,E]
     if g is not None:
@@ -173,7 +201,18 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
 
     import os
 
-    if q.is_cuda and N <= 128 and q.dtype == torch.float32 and os.environ.get("CO_TRAIN_ATTN", "fused") != "sdpa":
+    if remaining is not None:
+        # sdvrp: keys / values / logit keys of step t are the cached ones plus remaining_demand_t[n] * w (a Linear(1 -> 3E),
+        # dynamic.py:60-78, am/decoder.py:142-154).  Instead of T copies of K / V / L the rank-one term is applied where it
+        # lands: a per-(step, head) multiple of the remaining demand on the scores, the probability-weighted demand times
+        # w_v on the head outputs, and (glimpse . w_l) * demand on the logits
+        wk, wv, wl = dec.dynamic_embedding.projection.weight[:, 0].chunk(3)
+        qh, d = heads(q), remaining[:, None]                                                     # [B,H,Q,16], [B,1,Q,N]
+        scores = qh @ heads(K).transpose(-1, -2) + (qh * wk.view(1, H, 1, -1)).sum(-1, keepdim=True) * d
+        p = torch.softmax((scores / math.sqrt(E // H)).masked_fill(~mask[:, None], float("-inf")), -1)
+        o = p @ heads(V) + (p * d).sum(-1, keepdim=True) * wv.view(1, H, 1, -1)
+        o = o.transpose(1, 2).reshape(B, Q, E)
+    elif q.is_cuda and N <= 128 and q.dtype == torch.float32 and os.environ.get("CO_TRAIN_ATTN", "fused") != "sdpa":
         # the T (x S) decode steps of an instance are independent queries against its cached K / V: hand-written
         # masked attention forward / backward (co_attn_fwd / co_attn_bwd) on the cache's column views, no copies
         from . import attention_train
@@ -183,7 +222,10 @@ def evaluate_log_likelihood(policy, td: TensorDict, env, actions: torch.Tensor, 
         o = F.scaled_dot_product_attention(heads(q), heads(K), heads(V), attn_mask=mask[:, None])
         o = o.transpose(1, 2).reshape(B, Q, E)
     glimpse = dec.pointer.project_out(o)
-    logits = torch.bmm(glimpse, L.transpose(1, 2)) / math.sqrt(E)
+    logits = torch.bmm(glimpse, L.transpose(1, 2))
+    if remaining is not None:
+        logits = logits + (glimpse * wl).sum(-1, keepdim=True) * remaining
+    logits = logits / math.sqrt(E)
     clip = policy.tanh_clipping if tanh_clipping is None else tanh_clipping
     if clip > 0:
         logits = torch.tanh(logits) * clip

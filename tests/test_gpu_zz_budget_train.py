@@ -1,5 +1,5 @@
-"""GPU: REINFORCE glue of the orienteering / prize-collecting envs -- the differentiable one-call teacher-forced pass
-(reinforce.replay_budget_states + co_attn_fwd / co_attn_bwd) equals what the persistent rollout kernel reported for the
+"""GPU: REINFORCE glue of the orienteering / prize-collecting / split-delivery envs -- the differentiable one-call teacher-forced pass
+(reinforce.replay_budget_states + co_attn_fwd / co_attn_bwd; sdvrp: replay_split_delivery_states + rank-one dynamic terms) equals what the persistent rollout kernel reported for the
 same actions, and one training step runs end to end.  (Named to sort last: the kernels' own parity tests come first.)"""
 
 import pytest
@@ -23,7 +23,7 @@ def _setup(env_name, n, B, seed=0):
     return env, pol, td
 
 
-@pytest.mark.parametrize("env_name,n", [("op", 20), ("pctsp", 20), ("op", 50), ("pctsp", 50)])
+@pytest.mark.parametrize("env_name,n", [("op", 20), ("pctsp", 20), ("op", 50), ("pctsp", 50), ("sdvrp", 20), ("sdvrp", 50)])
 def test_differentiable_loglik_matches_kernel(env_name, n):
     from rl4co_b200.reinforce import evaluate_log_likelihood
 
@@ -36,7 +36,7 @@ def test_differentiable_loglik_matches_kernel(env_name, n):
     assert lp.requires_grad
 
 
-@pytest.mark.parametrize("env_name", ["op", "pctsp"])
+@pytest.mark.parametrize("env_name", ["op", "pctsp", "sdvrp"])
 def test_reinforce_step_runs(env_name):
     from rl4co_b200.reinforce import get_reinforce_baseline, reinforce_step
 

@@ -440,3 +440,40 @@ def test_teacher_forced_pass_budget_envs_cpu(golden, name):
     torch.testing.assert_close(lp, ref["logprobs"], rtol=1e-5, atol=2e-5)
     lp.sum().backward()   # the graph reaches the decoder weights
     assert pol.decoder.context_embedding.project_context.weight.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("name", ["am_sdvrp20", "am_sdvrp50"])
+def test_teacher_forced_pass_split_delivery_cpu(golden, name):
+    """SDVRP: the per-step dynamic embedding applied as rank-one terms on scores / head outputs / logits (no per-step
+    copies of K / V / L) reproduces the reference's recorded log-probabilities; masks bit for bit."""
+    from oracle import am_rollout_oracle as O
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+    from rl4co_b200.reinforce import evaluate_log_likelihood, replay_split_delivery_states
+    from rl4co_b200.tensordict import TensorDict
+
+    g = golden(name)
+    pol = FusedAttentionModelPolicy(env_name="sdvrp", num_encoder_layers=1).eval()
+    pol.load_state_dict({**pol.state_dict(), **g.weights()})
+    inst, h = g.inst(), g["h"]
+    B = h.shape[0]
+    env = get_env("sdvrp", generator_params=dict(num_loc=inst["locs"].shape[1]))
+    td = env.reset(TensorDict(inst, batch_size=[B]))
+    for mode in ("greedy", "sampling", "eval"):
+        lp = evaluate_log_likelihood(pol, td, env, g[f"{mode}_actions"], hidden=h, return_sum=False)
+        torch.testing.assert_close(lp, g[f"{mode}_logprobs"], rtol=1e-5, atol=2e-5)
+    mask = replay_split_delivery_states(td, g["greedy_actions"])[0]
+    assert torch.equal(mask.transpose(0, 1), g["greedy_masks"].bool())
+    gen = torch.Generator().manual_seed(5)
+    n = inst["locs"].shape[1]
+    inst2 = O.generate_instances("sdvrp", 64, n, generator=gen)
+    h2 = torch.randn(64, n + 1, 128, generator=gen)
+    with torch.no_grad():
+        ref = O.rollout(g.weights(), "sdvrp", inst2, h2, decode_type="sampling", temperature=20.0, generator=gen,
+                        return_trace=True)
+    td2 = env.reset(TensorDict(inst2, batch_size=[64]))
+    assert torch.equal(replay_split_delivery_states(td2, ref["actions"])[0], torch.stack(ref["trace"]["mask"], 1))
+    lp = evaluate_log_likelihood(pol, td2, env, ref["actions"], hidden=h2, return_sum=False, temperature=20.0)
+    torch.testing.assert_close(lp, ref["logprobs"], rtol=1e-5, atol=2e-5)
+    lp.sum().backward()
+    assert pol.decoder.dynamic_embedding.projection.weight.grad.abs().sum() > 0

@@ -14,7 +14,7 @@ from rl4co_b200.reinforce import get_reinforce_baseline, reinforce_step
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda:0")
-for env_name in ("cvrp", "op", "pctsp"):
+for env_name in ("cvrp", "sdvrp", "op", "pctsp"):
     torch.manual_seed(0)
     env = get_env(env_name, generator_params=dict(num_loc=N), check_solution=False)
     pol = FusedAttentionModelPolicy(env_name=env_name).to(dev)
