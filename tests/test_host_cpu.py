@@ -477,3 +477,32 @@ def test_teacher_forced_pass_split_delivery_cpu(golden, name):
     torch.testing.assert_close(lp, ref["logprobs"], rtol=1e-5, atol=2e-5)
     lp.sum().backward()
     assert pol.decoder.dynamic_embedding.projection.weight.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("name", ["am_tsp20", "am_cvrp20", "am_op20", "am_pctsp20"])
+def test_teacher_forced_pass_multistart_cpu(golden, name):
+    """POMO-style training: S forced start nodes per instance become S * T queries against one K / V; start-major
+    [S * B, T] actions in, the oracle's multistart log-probabilities out (the start column carries 0)."""
+    from conftest import env_of
+    from oracle import am_rollout_oracle as O
+    from rl4co_b200.envs import get_env
+    from rl4co_b200.policy import FusedAttentionModelPolicy
+    from rl4co_b200.reinforce import evaluate_log_likelihood
+    from rl4co_b200.tensordict import TensorDict
+
+    g = golden(name)
+    env_name = env_of(name)
+    pol = FusedAttentionModelPolicy(env_name=env_name, num_encoder_layers=1).eval()
+    pol.load_state_dict({**pol.state_dict(), **g.weights()})
+    gen = torch.Generator().manual_seed(3)
+    n = g.inst()["locs"].shape[1]
+    inst = O.generate_instances(env_name, 12, n, generator=gen)
+    h = torch.randn(12, n + (0 if env_name == "tsp" else 1), 128, generator=gen)
+    with torch.no_grad():
+        ref = O.rollout(g.weights(), env_name, inst, h, decode_type="multistart_sampling", num_starts=5, temperature=20.0,
+                        generator=gen)
+    env = get_env(env_name, generator_params=dict(num_loc=n))
+    td = env.reset(TensorDict(inst, batch_size=[12]))
+    lp = evaluate_log_likelihood(pol, td, env, ref["actions"], hidden=h, return_sum=False, temperature=20.0)
+    torch.testing.assert_close(lp, ref["logprobs"], rtol=1e-5, atol=2e-5)
+    assert (lp[:, 0] == 0).all()
