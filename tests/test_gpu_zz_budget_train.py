@@ -1,6 +1,7 @@
-"""GPU: REINFORCE glue of the orienteering / prize-collecting / split-delivery envs -- the differentiable one-call teacher-forced pass
-(reinforce.replay_budget_states + co_attn_fwd / co_attn_bwd; sdvrp: replay_split_delivery_states + rank-one dynamic terms) equals what the persistent rollout kernel reported for the
-same actions, and one training step runs end to end.  (Named to sort last: the kernels' own parity tests come first.)"""
+"""GPU: REINFORCE glue of the orienteering / prize-collecting / split-delivery envs -- the differentiable one-call
+teacher-forced pass (reinforce.replay_budget_states + co_attn_fwd / co_attn_bwd; sdvrp: replay_split_delivery_states +
+rank-one dynamic terms) equals what the persistent rollout kernel reported for the same actions, and one training step
+runs end to end.  (Named to sort last: the kernels' own parity tests come first.)"""
 
 import pytest
 import torch
